@@ -1,0 +1,201 @@
+/* hdn.h -- C-ABI of libhdn.so, the sm_100a kernel library behind the H-DenseUNet engine.
+ *
+ * The reference (xmengli/H-DenseUNet) has no FFI of its own: its hot path is Keras-2.0.8
+ * Python calling TensorFlow ops.  Each entry point below replaces the TF op(s) named in
+ * its comment (KB = Keras-2.0.8/keras/backend/tensorflow_backend.py in the reference).
+ *
+ * Conventions
+ *   - plain C: POD descriptors, raw device pointers, sizes; no C++/torch types.
+ *   - every call returns 0 on success, a negative hdn_status on error; the message is
+ *     available from hdn_last_error() (thread-local).  Nothing throws.
+ *   - all buffers are caller-owned device memory; launches go to the given cudaStream_t
+ *     (passed as void*).  The library keeps no global mutable state except the error string.
+ *   - activations are fp32, channels-last 5-D  (N, D, H, W, C); a 2-D tensor has D == 1.
+ *     Reference 3-D tensors (N,H,W,S,C) map to D = S (slice axis outermost), which makes the
+ *     2-D network's (S,H,W,C) output *be* the 3-D network's input without a copy
+ *     (hybridnet.py:355-411).  A tensor argument is a channel window of a wider buffer:
+ *     element (n,d,h,w,c) lives at  base[(((n*D+d)*H+h)*W+w)*ldc + coff + c].
+ *   - conv weights are [kd][kh][kw][Cin][Cout] fp32 (Keras HWIO / DHWIO with the slice axis
+ *     moved first).
+ */
+#ifndef HDN_H_
+#define HDN_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  HDN_OK = 0,
+  HDN_ERR_ARG = -1,      /* bad descriptor (shape / pointer / alignment) */
+  HDN_ERR_CUDA = -2,     /* CUDA runtime error (message carries cudaGetErrorString) */
+  HDN_ERR_UNSUPPORTED = -3
+} hdn_status;
+
+const char* hdn_last_error(void);
+int hdn_version(void);
+
+typedef struct {
+  const float* p;   /* base pointer (device) */
+  int ldc;          /* channel stride of the underlying buffer (elements) */
+  int coff;         /* first channel of the window */
+} hdn_tensor;
+
+/* One A-operand source of a convolution: a stored tensor, an optional per-channel
+ * affine + ReLU applied on load (BatchNorm -> Scale -> ReLU folded to y = max(a*x+b,0),
+ * KB:1684 + lib/custom_layers.py:68 + KB:2671), and nearest-neighbour up-sampling factors
+ * (UpSampling2D/3D, KB:1764-1771,1797-1827) folded into the load index. */
+typedef struct {
+  hdn_tensor t;
+  int D, H, W;            /* stored (pre-upsample) spatial dims */
+  int ud, uh, uw;         /* upsample factors, 1 or 2 */
+  const float* pa;        /* [Cin] scale, NULL => 1 */
+  const float* pb;        /* [Cin] shift, NULL => 0 */
+  int relu;
+} hdn_src;
+
+/* Convolution geometry.  Output position (n,od,oh,ow) reads the (virtually up-sampled,
+ * zero-padded) input at (od*sd - pd + kd_i, ...).  Replaces ZeroPadding + tf.nn.convolution
+ * (KB:2020, KB:3158, KB:3307) and, with nsrc == 2, the Add merge in front of it
+ * (merge.py:207-211): A = f1(src[0]) + f2(src[1]). */
+typedef struct {
+  int N, D, H, W;         /* output grid */
+  int Cin, Cout;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int nsrc;
+  hdn_src src[2];
+  const float* w;         /* [kd][kh][kw][Cin][Cout] */
+  const float* bias;      /* [Cout] or NULL (KB:3480) */
+  hdn_tensor y;           /* output window (fprop) / dY window (dgrad, wgrad) */
+  double* stat_sum;       /* [Cout] += sum_m y, or NULL  (feeds tf.nn.moments, KB:1635) */
+  double* stat_sq;        /* [Cout] += sum_m y^2 */
+  float drop_keep;        /* 1.0 => no dropout; else y = y*mask/keep (KB:2888) */
+  uint64_t drop_seed;
+  int precision;          /* 0: fp32 FMA (parity path)  1: tcgen05 bf16 operands, fp32 accumulate */
+} hdn_conv;
+
+/* Epilogue of a data-gradient: given dz = dL/d(prologue output) it forms
+ * du = dz * [a*x+b > 0] (ReLU backward), accumulates S1[c] += sum du, S2[c] += sum du*(x-center[c])
+ * (everything the BN / Scale parameter gradients need; center = the BN mean keeps the sums
+ * free of cancellation), and then either
+ *   mode 0: dx (+)= a[c] * du            (inference-mode BN: the affine is a constant)
+ *   mode 1: du_out (+)= du               (training-mode BN: hdn_bn_bwd_apply finishes it)
+ *   mode 2: this source needs no gradient; skipped */
+typedef struct {
+  hdn_tensor dx;          /* gradient window of the stored source (mode 0) */
+  float* du;              /* dense [M_src][Cin] (mode 1) */
+  int mode;
+  int accumulate;         /* 0: overwrite, 1: += */
+  double* s1;             /* [Cin] or NULL */
+  double* s2;
+  const float* center;    /* [Cin] or NULL (=> 0) */
+} hdn_dgrad_epi;
+
+int hdn_conv_fprop(const hdn_conv* c, void* stream);
+/* dgrad: c->y is dY.  One epilogue per source. */
+int hdn_conv_dgrad(const hdn_conv* c, const hdn_dgrad_epi* epi, void* stream);
+/* wgrad: dw [kd][kh][kw][Cin][Cout] += A^T dY ; dbias [Cout] += sum_m dY (NULL to skip). */
+int hdn_conv_wgrad(const hdn_conv* c, float* dw, float* dbias, void* stream);
+/* 1 if the tcgen05 path (precision == 1) takes this descriptor for the given pass, else 0. */
+int hdn_conv_tc_supported(const hdn_conv* c, int pass /*0 fprop 1 dgrad 2 wgrad*/);
+
+/* Pooling (KB:3354-3432).  kind 0: max 3x3(x3)/2 after zero-pad 1 (the ZeroPadding + VALID
+ * max-pool of hybridnet.py:128-129,215-216; input passes through the src prologue first);
+ * kind 1: average 2x2 stride 2 over H,W (AveragePooling2D (2,2) / AveragePooling3D (2,2,1)). */
+typedef struct {
+  int kind;
+  int N, D, H, W, C;      /* output grid */
+  int pool_d;             /* kind 0: 1 => also pool depth (3-D), 0 => 2-D */
+  hdn_src src;
+  hdn_tensor y;           /* output (fwd) / dY (bwd) */
+} hdn_pool;
+int hdn_pool_fwd(const hdn_pool* p, void* stream);
+int hdn_pool_bwd(const hdn_pool* p, const hdn_dgrad_epi* epi, void* stream);
+
+/* BatchNorm (+ optional Scale) folding.  mode 1 = training statistics from (sum, sumsq, count),
+ * biased variance, and moving-average update  mov -= (mov-batch)*(1-momentum)  (KB:1635,
+ * KNORM:179-185, KB:915-927);  mode 0 = moving statistics (KB:1684).
+ * Produces a = gs*g*rstd, b = gs*(beta - mean*g*rstd) + bs, and saves mean / rstd. */
+typedef struct {
+  int C, mode;
+  double count;
+  const double* sum; const double* sumsq;
+  float* mov_mean; float* mov_var;
+  const float* gamma; const float* beta;       /* BN */
+  const float* sgamma; const float* sbeta;     /* Scale or NULL */
+  float eps, momentum;
+  float* a; float* b; float* mean; float* rstd;
+} hdn_bn_fold_t;
+int hdn_bn_fold(const hdn_bn_fold_t* f, void* stream);
+
+/* Parameter gradients of BN/Scale from S1 = sum du, S2 = sum du*(x-mean); in training mode also
+ * the per-channel coefficients (k0,k1,k2) with dx = k0*du + k1*(x-mean) + k2 used by
+ * hdn_bn_bwd_apply. */
+typedef struct {
+  int C, mode;
+  double count;
+  const double* s1; const double* s2;
+  const float* mean; const float* rstd;
+  const float* gamma; const float* beta; const float* sgamma;
+  float* dgamma; float* dbeta; float* dsgamma; float* dsbeta;   /* += ; any may be NULL */
+  float* k0; float* k1; float* k2;                               /* training mode only */
+} hdn_bn_grad_t;
+int hdn_bn_param_grad(const hdn_bn_grad_t* g, void* stream);
+/* dx (+)= k0[c]*du[m][c] + k1[c]*(x[m][c]-mean[c]) + k2[c] over M rows. */
+int hdn_bn_bwd_apply(const float* du, hdn_tensor x, hdn_tensor dx, int64_t M, int C,
+                     const float* k0, const float* k1, const float* k2, const float* mean,
+                     int accumulate, void* stream);
+
+/* Per-channel sum and sum of squares of a window (batch statistics of pooled features that
+ * no convolution epilogue produced): sum[c] += sum_m y, sq[c] += sum_m y^2. */
+int hdn_col_stats(hdn_tensor y, int64_t M, int C, double* sum, double* sq, void* stream);
+
+/* In-place dropout backward on a gradient window: g *= mask/keep (same hash as fprop). */
+int hdn_dropout_bwd(hdn_tensor g, int64_t M, int C, float keep, uint64_t seed, void* stream);
+
+/* Weighted soft-max cross entropy, forward + gradient in one pass (loss.py:5-46).
+ * logits/dlogits (N,D,H,W,3); labels float (N,D,H,W); only depth d in [d0,d1) counts
+ * (loss.py:6-7 crop).  Pass 1 accumulates acc[0] = sum w*log p, acc[1] = #counted voxels;
+ * pass 2 writes dlogits = w[y]*(p - onehot)*[p_y >= 1e-10] / count * gscale. */
+int hdn_wce_accum(const float* logits, const float* labels, int64_t N, int D, int64_t HW,
+                  int d0, int d1, double* acc, void* stream);
+int hdn_wce_grad(const float* logits, const float* labels, float* dlogits, int64_t N, int D,
+                 int64_t HW, int d0, int d1, const double* acc, float gscale, void* stream);
+
+/* Hybrid glue (hybridnet.py:385-396, 409-411).
+ * triplets: vol (B,S,H,W) -> out (B*S,1,H,W,3), channel k of slice s = vol[clamp(s-1+k)].
+ * cat4:     out (B,S,H,W,4) = [vol, 250*logits2d(3)];  cat4_bwd: dlogits += 250*dout[...,1:4]. */
+int hdn_triplets(const float* vol, float* out, int B, int S, int64_t HW, void* stream);
+int hdn_cat4(const float* vol, const float* logits, float* out, int64_t M, float k, void* stream);
+int hdn_cat4_bwd(const float* dout, float* dlogits, int64_t M, float k, int accumulate, void* stream);
+
+/* Nesterov SGD over a flat arena (optimizers.py:172-181): v = mu*m - lr*g*gs; m = v;
+ * p += mu*v - lr*g*gs. */
+int hdn_sgd_nesterov(float* p, const float* g, float* m, int64_t n, float lr, float mu,
+                     float gscale, void* stream);
+/* Data-parallel step over NVLink peer memory: rank r owns elements [lo,hi) of the flat
+ * arena, sums the `world` peer gradient arenas (peer_g[i] are peer-mapped device pointers),
+ * applies the Nesterov update to its shard and pushes the updated parameters into every
+ * peer's parameter arena (replaces multi_gpu.py:7-69 + the implicit TF gradient sum). */
+int hdn_dp_reduce_sgd(float* const* peer_p, const float* const* peer_g, float* m_local,
+                      int world, int rank, int64_t lo, int64_t hi, float lr, float mu,
+                      float gscale, void* stream);
+
+/* Sliding-window accumulation (lib/funcs.py:28-47): softmax over 3 logits of a window
+ * (1,S,H,W,3), slices 1..S-2 added into score (Z,H,W,2) [classes 1,2] and count (Z) at z0+1. */
+int hdn_window_accumulate(const float* logits, float* score, int* count, int S, int64_t HW,
+                          int z0, void* stream);
+int hdn_window_finalize(float* score, const int* count, int Z, int64_t HW, void* stream);
+
+/* Raw device memory + CUDA IPC for the parameter / gradient arenas that the per-GPU
+ * processes map into each other (handle = 64 bytes, cudaIpcMemHandle_t). */
+int hdn_dev_malloc(void** out, int64_t bytes);
+int hdn_dev_free(void* p);
+int hdn_ipc_get_handle(void* p, unsigned char* handle64);
+int hdn_ipc_open(const unsigned char* handle64, void** out);
+int hdn_ipc_close(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -121,6 +121,27 @@ class CudaBackend(object):
     def __init__(self):
         self.lib = _lib.load()
         self.launches = 0
+        self.prof = None          # list of (key, flops, start_event, end_event) while profiling
+
+    def _run(self, key, flops, n_launch, fn, *args):
+        """Issue one C-ABI call; with profiling on, bracket it with CUDA events on the launch stream."""
+        self.launches += n_launch
+        if self.prof is None:
+            return fn(*args)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn(*args)
+        e.record()
+        self.prof.append((key, flops, s, e))
+        return rc
+
+    @staticmethod
+    def _conv_key(d, what):
+        return "conv_%s[%s] k%dx%dx%d" % (what, "tc" if d.precision else "simt", d.k[0], d.k[1], d.k[2])
+
+    @staticmethod
+    def _conv_flops(d):
+        return 2.0 * d.out.M * d.Cin * d.Cout * d.k[0] * d.k[1] * d.k[2]
 
     @property
     def stream(self):
@@ -180,8 +201,8 @@ class CudaBackend(object):
         return bool(self.lib.hdn_conv_tc_supported(C.byref(self._conv(d)), which))
 
     def conv_fprop(self, d):
-        self.launches += 1
-        _lib.check(self.lib.hdn_conv_fprop(C.byref(self._conv(d)), self.stream), "hdn_conv_fprop " + d.name)
+        _lib.check(self._run(self._conv_key(d, "fprop"), self._conv_flops(d), 1, self.lib.hdn_conv_fprop,
+                             C.byref(self._conv(d)), self.stream), "hdn_conv_fprop " + d.name)
 
     def conv_dgrad(self, d, epis):
         arr = d.__dict__.get("_c_epis")
@@ -190,13 +211,14 @@ class CudaBackend(object):
             for i, e in enumerate(epis):
                 arr[i] = self._epi(e, d.Cin)
             d.__dict__["_c_epis"] = arr
-        self.launches += len(epis)
-        _lib.check(self.lib.hdn_conv_dgrad(C.byref(self._conv(d, True)), arr, self.stream), "hdn_conv_dgrad " + d.name)
+        nact = sum(1 for e in epis if e.mode != 2)
+        _lib.check(self._run(self._conv_key(d, "dgrad"), self._conv_flops(d) * nact, nact, self.lib.hdn_conv_dgrad,
+                             C.byref(self._conv(d, True)), arr, self.stream), "hdn_conv_dgrad " + d.name)
 
     def conv_wgrad(self, d, dw, dbias):
-        self.launches += 1 + (dbias is not None)
-        _lib.check(self.lib.hdn_conv_wgrad(C.byref(self._conv(d, True)), dw.data_ptr(), _ptr(dbias), self.stream),
-                   "hdn_conv_wgrad " + d.name)
+        _lib.check(self._run(self._conv_key(d, "wgrad"), self._conv_flops(d), 1 + (dbias is not None),
+                             self.lib.hdn_conv_wgrad, C.byref(self._conv(d, True)), dw.data_ptr(), _ptr(dbias),
+                             self.stream), "hdn_conv_wgrad " + d.name)
 
     def _pool(self, d, y_grad):
         key = "_c_g" if y_grad else "_c_f"
@@ -212,17 +234,14 @@ class CudaBackend(object):
         return c
 
     def pool_fwd(self, d):
-        self.launches += 1
-        _lib.check(self.lib.hdn_pool_fwd(C.byref(self._pool(d, False)), self.stream), "hdn_pool_fwd")
+        _lib.check(self._run("pool_fwd", 0.0, 1, self.lib.hdn_pool_fwd, C.byref(self._pool(d, False)), self.stream), "hdn_pool_fwd")
 
     def pool_bwd(self, d, epi):
-        self.launches += 1
-        _lib.check(self.lib.hdn_pool_bwd(C.byref(self._pool(d, True)), C.byref(self._epi(epi, d.out.C)), self.stream),
+        _lib.check(self._run("pool_bwd", 0.0, 1, self.lib.hdn_pool_bwd, C.byref(self._pool(d, True)), C.byref(self._epi(epi, d.out.C)), self.stream),
                    "hdn_pool_bwd")
 
     def col_stats(self, view, stat):
-        self.launches += 1
-        _lib.check(self.lib.hdn_col_stats(self._tensor(view), view.M, view.C, stat[0].data_ptr(), stat[1].data_ptr(),
+        _lib.check(self._run("col_stats", 0.0, 1, self.lib.hdn_col_stats, self._tensor(view), view.M, view.C, stat[0].data_ptr(), stat[1].data_ptr(),
                                           self.stream), "hdn_col_stats")
 
     def bn_fold(self, f, mode):
@@ -239,8 +258,7 @@ class CudaBackend(object):
             c.eps, c.momentum = f.eps, f.momentum
             c.a, c.b, c.mean, c.rstd = f.a.data_ptr(), f.b.data_ptr(), f.mean.data_ptr(), f.rstd.data_ptr()
             f.__dict__["_c_fold%d" % mode] = c
-        self.launches += 1
-        _lib.check(self.lib.hdn_bn_fold(C.byref(c), self.stream), "hdn_bn_fold " + f.name)
+        _lib.check(self._run("bn_fold", 0.0, 1, self.lib.hdn_bn_fold, C.byref(c), self.stream), "hdn_bn_fold " + f.name)
 
     def bn_param_grad(self, f, mode):
         c = f.__dict__.get("_c_grad")
@@ -258,57 +276,46 @@ class CudaBackend(object):
             if mode == 1:
                 c.k0, c.k1, c.k2 = f.k[0].data_ptr(), f.k[1].data_ptr(), f.k[2].data_ptr()
             f.__dict__["_c_grad"] = c
-        self.launches += 1
-        _lib.check(self.lib.hdn_bn_param_grad(C.byref(c), self.stream), "hdn_bn_param_grad " + f.name)
+        _lib.check(self._run("bn_param_grad", 0.0, 1, self.lib.hdn_bn_param_grad, C.byref(c), self.stream), "hdn_bn_param_grad " + f.name)
 
     def bn_bwd_apply(self, f, accumulate):
         v = f.view
-        self.launches += 1
-        _lib.check(self.lib.hdn_bn_bwd_apply(f.du.data_ptr(), self._tensor(v), self._tensor(v, True), v.M, v.C,
+        _lib.check(self._run("bn_bwd_apply", 0.0, 1, self.lib.hdn_bn_bwd_apply, f.du.data_ptr(), self._tensor(v), self._tensor(v, True), v.M, v.C,
                                              f.k[0].data_ptr(), f.k[1].data_ptr(), f.k[2].data_ptr(),
                                              f.mean.data_ptr(), 1 if accumulate else 0, self.stream), "hdn_bn_bwd_apply " + f.name)
 
     def dropout_bwd(self, view, keep, seed):
-        self.launches += 1
-        _lib.check(self.lib.hdn_dropout_bwd(self._tensor(view, True), view.M, view.C, keep, seed, self.stream),
+        _lib.check(self._run("dropout_bwd", 0.0, 1, self.lib.hdn_dropout_bwd, self._tensor(view, True), view.M, view.C, keep, seed, self.stream),
                    "hdn_dropout_bwd")
 
     def wce_accum(self, logits, labels, N, D, HW, d0, d1, acc):
-        self.launches += 1
-        _lib.check(self.lib.hdn_wce_accum(logits.data_ptr(), labels.data_ptr(), N, D, HW, d0, d1, acc.data_ptr(),
+        _lib.check(self._run("wce_accum", 0.0, 1, self.lib.hdn_wce_accum, logits.data_ptr(), labels.data_ptr(), N, D, HW, d0, d1, acc.data_ptr(),
                                           self.stream), "hdn_wce_accum")
 
     def wce_grad(self, logits, labels, dlogits, N, D, HW, d0, d1, acc, gscale):
-        self.launches += 1
-        _lib.check(self.lib.hdn_wce_grad(logits.data_ptr(), labels.data_ptr(), dlogits.data_ptr(), N, D, HW, d0, d1,
+        _lib.check(self._run("wce_grad", 0.0, 1, self.lib.hdn_wce_grad, logits.data_ptr(), labels.data_ptr(), dlogits.data_ptr(), N, D, HW, d0, d1,
                                          acc.data_ptr(), gscale, self.stream), "hdn_wce_grad")
 
     def triplets(self, vol, out, B, S, HW):
-        self.launches += 1
-        _lib.check(self.lib.hdn_triplets(vol.data_ptr(), out.data_ptr(), B, S, HW, self.stream), "hdn_triplets")
+        _lib.check(self._run("triplets", 0.0, 1, self.lib.hdn_triplets, vol.data_ptr(), out.data_ptr(), B, S, HW, self.stream), "hdn_triplets")
 
     def cat4(self, vol, logits, out, M, k):
-        self.launches += 1
-        _lib.check(self.lib.hdn_cat4(vol.data_ptr(), logits.data_ptr(), out.data_ptr(), M, k, self.stream), "hdn_cat4")
+        _lib.check(self._run("cat4", 0.0, 1, self.lib.hdn_cat4, vol.data_ptr(), logits.data_ptr(), out.data_ptr(), M, k, self.stream), "hdn_cat4")
 
     def cat4_bwd(self, dout, dlogits, M, k, accumulate):
-        self.launches += 1
-        _lib.check(self.lib.hdn_cat4_bwd(dout.data_ptr(), dlogits.data_ptr(), M, k, 1 if accumulate else 0,
+        _lib.check(self._run("cat4_bwd", 0.0, 1, self.lib.hdn_cat4_bwd, dout.data_ptr(), dlogits.data_ptr(), M, k, 1 if accumulate else 0,
                                          self.stream), "hdn_cat4_bwd")
 
     def sgd(self, p, g, m, n, lr, mu, gscale):
-        self.launches += 1
-        _lib.check(self.lib.hdn_sgd_nesterov(p.data_ptr(), g.data_ptr(), m.data_ptr(), n, lr, mu, gscale, self.stream),
+        _lib.check(self._run("sgd_nesterov", 0.0, 1, self.lib.hdn_sgd_nesterov, p.data_ptr(), g.data_ptr(), m.data_ptr(), n, lr, mu, gscale, self.stream),
                    "hdn_sgd_nesterov")
 
     def window_accumulate(self, logits, score, count, S, HW, z0):
-        self.launches += 2
-        _lib.check(self.lib.hdn_window_accumulate(logits.data_ptr(), score.data_ptr(), count.data_ptr(), S, HW, z0,
+        _lib.check(self._run("window_accumulate", 0.0, 2, self.lib.hdn_window_accumulate, logits.data_ptr(), score.data_ptr(), count.data_ptr(), S, HW, z0,
                                                   self.stream), "hdn_window_accumulate")
 
     def window_finalize(self, score, count, Z, HW):
-        self.launches += 1
-        _lib.check(self.lib.hdn_window_finalize(score.data_ptr(), count.data_ptr(), Z, HW, self.stream),
+        _lib.check(self._run("window_finalize", 0.0, 1, self.lib.hdn_window_finalize, score.data_ptr(), count.data_ptr(), Z, HW, self.stream),
                    "hdn_window_finalize")
 
 

@@ -1,0 +1,186 @@
+"""GPU parity tests proper: whole programs through the C-ABI (libhdn.so) on a B200 against
+  (1) the CPU oracle (oracle/hdense_oracle.py) -- logits / loss / every parameter gradient, and
+  (2) the plain-PyTorch reference backend run on the same device with the same parameters.
+Tolerances: fp32 path logits rel-L2 <= 1e-3 (north-star bound; measured ~1e-5), loss rel <= 1e-3,
+gradients rel-L2 <= max(5e-3, 8x the fp32 oracle's own distance from the fp64 oracle)."""
+import numpy as np
+import pytest
+import torch
+
+import h_denseunet_b200 as hdn
+from oracle import hdense_oracle as orc
+from torch_backend import TorchBackend
+from util import Args, perturb_params, rel_l2, synthetic_slab
+
+pytestmark = pytest.mark.gpu
+
+
+def _grad_check(eg, og32, og64, names, floor):
+    bad, n = [], 0
+    for k in names:
+        if og64.get(k) is None:
+            assert np.abs(eg[k]).max() == 0, k
+            continue
+        if np.abs(og64[k]).max() < 1e-9:
+            continue
+        n += 1
+        e = rel_l2(eg[k], og64[k])
+        tol = max(floor, 8.0 * rel_l2(og32[k], og64[k]))
+        if e > tol:
+            bad.append((k, e, tol))
+    assert not bad, "gradient mismatch (name, err, tol): %s" % bad[:10]
+    return n
+
+
+def _oracle_2d(w0, x, y, skip):
+    out = {}
+    for dt in (torch.float32, torch.float64):
+        ctx, _, logits = orc.forward_2d(w0, x, training=True, learn_bn=True, skip=skip, requires_grad=True, dtype=dt)
+        loss = orc.weighted_crossentropy(torch.as_tensor(y), logits, crop=False)
+        out[dt] = (logits.detach().numpy(), float(loss.detach()), orc.grads_of(ctx, loss))
+    return out
+
+
+@pytest.mark.parametrize("skip", [False, True])
+def test_unet2d_train_step_fp32(cuda_dev, skip):
+    a = Args(b=2, input_size=64)
+    m = hdn.DenseUNet(reduction=0.5, args=a, skip=skip, precision="fp32")
+    m.dropout = False
+    perturb_params(m)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy_2ddense])
+    rng = np.random.default_rng(0)
+    x = rng.normal(0, 60, (2, 64, 64, 3)).astype(np.float32)
+    y = rng.integers(0, 3, (2, 64, 64, 1)).astype(np.int16)
+    w0 = m.get_weights_dict()
+    o = _oracle_2d(w0, x, y, skip)
+    loss = m.train_on_batch(x, y)
+    net = m.nets[True]
+    assert net.be.name == "cuda" and net.be.launches > 500
+    got = m._logits_to_host(net)
+    assert rel_l2(got, o[torch.float32][0]) < 1e-3
+    assert abs(loss - o[torch.float32][1]) <= 1e-3 * abs(o[torch.float32][1])
+    n = _grad_check(m.get_grads_dict(), o[torch.float32][2], o[torch.float64][2], m.get_grads_dict().keys(), 5e-3)
+    assert n > 50
+    # Nesterov update (optimizers.py:172-181) applied by hdn_sgd_nesterov
+    w1 = m.get_weights_dict()
+    g = m.get_grads_dict()
+    for k in ["conv1/kernel", "conv3_5_x2/kernel", "conv_up2/bias", "conv4_7_x1_scale/gamma", "bn_up3/beta"]:
+        p1, _ = orc.sgd_nesterov_step(w0[k], g[k], np.zeros_like(w0[k]))
+        assert np.allclose(w1[k], p1, atol=1e-7, rtol=1e-5), k
+
+
+@pytest.mark.parametrize("variant", ["end2end", "3dpart"])
+def test_hybrid_train_step_fp32(cuda_dev, variant):
+    a = Args(b=1, input_size=64, input_cols=8)
+    build = hdn.dense_rnn_net if variant == "end2end" else hdn.denseunet_3d
+    m = build(a, precision="fp32")
+    m.dropout = False
+    perturb_params(m)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+    vol, lab = synthetic_slab(1, 64, 8)
+    w0 = m.get_weights_dict()
+    og, ol, olog = {}, {}, {}
+    for dt in (torch.float32, torch.float64):
+        ctx, logits = orc.forward_hybrid(w0, vol, training=True, variant=variant, requires_grad=True, dtype=dt)
+        loss = orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), logits, crop=True)
+        og[dt], ol[dt], olog[dt] = orc.grads_of(ctx, loss), float(loss.detach()), logits.detach().numpy()
+    loss = m.train_on_batch(vol, lab)
+    net = m.nets[True]
+    got = m._logits_to_host(net)
+    assert rel_l2(got, olog[torch.float32]) < 1e-3
+    assert abs(loss - ol[torch.float32]) <= 1e-3 * abs(ol[torch.float32])
+    trainable = sorted(p.name for p in m.params.order if p.trainable)
+    _grad_check(m.get_grads_dict(), og[torch.float32], og[torch.float64], trainable,
+                5e-2 if variant == "3dpart" else 5e-3)
+    # inference program (moving statistics, no dropout) shares the parameters
+    out = m.predict(vol)
+    _, l2 = orc.forward_hybrid(m.get_weights_dict(), vol, training=False, variant=variant)
+    assert rel_l2(out, l2.numpy()) < 1e-3
+    # Dice of the argmax / thresholded masks identical to 4 d.p. (test.py:34-35,73-77)
+    pe = torch.softmax(torch.as_tensor(out), -1).numpy()
+    po = torch.softmax(l2, -1).numpy()
+    for cls, thr in ((1, 0.5), (2, 0.9)):
+        de = orc.dice(pe[..., cls] > thr, lab[..., 0] == cls)
+        do = orc.dice(po[..., cls] > thr, lab[..., 0] == cls)
+        assert round(de, 4) == round(do, 4)
+
+
+def test_cuda_matches_torch_backend_same_device(cuda_dev):
+    """Same program, same parameters, same device: libhdn.so vs the plain-PyTorch backend --
+    every activation buffer, every gradient buffer, every parameter gradient."""
+    a = Args(b=1, input_size=64, input_cols=8)
+    vol, lab = synthetic_slab(1, 64, 8, seed=5)
+    ms = []
+    for be in (None, TorchBackend()):
+        m = hdn.dense_rnn_net(a, precision="fp32", backend=be)
+        m.dropout = False
+        perturb_params(m)
+        m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+        m.train_on_batch(vol, lab)
+        ms.append(m)
+    n0, n1 = ms[0].nets[True], ms[1].nets[True]
+    worst = 0.0
+    for b0, b1 in zip(n0.buffers, n1.buffers):
+        e = rel_l2(b0.data.cpu().numpy(), b1.data.cpu().numpy())
+        worst = max(worst, e)
+        assert e < 1e-4, (b0.name, e)
+    g0, g1 = ms[0].get_grads_dict(), ms[1].get_grads_dict()
+    for k in g0:
+        if np.abs(g1[k]).max() < 1e-9:
+            continue
+        assert rel_l2(g0[k], g1[k]) < 2e-3, k
+
+
+def test_net3d_config3_shape_fp32(cuda_dev):
+    """BASELINE config 3 topology (3-D DenseNet + head) at a reduced 64x64x8 volume: fwd+bwd vs oracle."""
+    a = Args(b=1, input_size=64, input_cols=8)
+    m = hdn.DenseNet3D(a, precision="fp32")
+    m.dropout = False
+    perturb_params(m)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+    rng = np.random.default_rng(3)
+    x = rng.normal(0, 50, (1, 64, 64, 8, 4)).astype(np.float32)
+    y = rng.integers(0, 3, (1, 64, 64, 8, 1)).astype(np.int16)
+    loss = m.train_on_batch(x, y)
+    assert np.isfinite(loss)
+    net = m._net(False)
+    m._upload(net, x)
+    net.forward()
+    f = net.outputs["feature3d"]
+    got = torch.relu(f.view.buf.data * f.fold.a + f.fold.b).permute(0, 2, 3, 1, 4).cpu().numpy()
+    _, exp = orc.forward_3d(m.get_weights_dict(), x, training=False)
+    assert rel_l2(got, exp.numpy()) < 1e-3
+
+
+def test_dropout_mask_is_consistent(cuda_dev):
+    """Dropout (KB:2888) on: forward mask and backward mask come from the same stateless hash; the kept
+    fraction matches keep_prob and dropped outputs are exactly zero."""
+    a = Args(b=1, input_size=64, input_cols=8)
+    m = hdn.dense_rnn_net(a, precision="fp32")
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+    vol, lab = synthetic_slab(1, 64, 8)
+    loss = m.train_on_batch(vol, lab)
+    assert np.isfinite(loss)
+    net = m.nets[True]
+    y = [b for b in net.buffers if b.name == "fianl_conv"][0].data
+    frac = float((y == 0).float().mean())
+    assert abs(frac - 0.3) < 0.02, frac
+
+
+def test_sliding_window_matches_oracle(cuda_dev):
+    """lib/funcs.py:4-51 on a small volume: window list, soft-max, edge-slice drop, overlap averaging."""
+    a = Args(b=1, input_size=32, input_cols=8)
+    m = hdn.dense_rnn_net(a, precision="fp32")
+    perturb_params(m)
+    rng = np.random.default_rng(11)
+    vol = rng.normal(0, 60, (32, 32, 20)).astype(np.float32)
+    mini, maxi = np.array([0, 0, 4]), np.array([31, 31, 15])
+    s1, s2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a)
+    w = m.get_weights_dict()
+
+    def pred(box):
+        return orc.forward_hybrid(w, box, training=False)[1].numpy()
+
+    o1, o2 = orc.predict_tumor_inwindow(pred, vol, 3, mini, maxi, 32, 8)
+    assert np.abs(s1 - o1).max() < 2e-3 and np.abs(s2 - o2).max() < 2e-3
+    assert rel_l2(s1, o1) < 1e-3

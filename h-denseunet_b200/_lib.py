@@ -53,7 +53,8 @@ class Conv(C.Structure):
                 ("nsrc", C.c_int), ("src", Src * 2),
                 ("w", C.c_void_p), ("bias", C.c_void_p), ("y", Tensor),
                 ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p),
-                ("drop_keep", C.c_float), ("drop_seed", C.c_uint64), ("precision", C.c_int)]
+                ("drop_keep", C.c_float), ("drop_seed", C.c_uint64), ("precision", C.c_int),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_int64)]
 
 
 class DgradEpi(C.Structure):
@@ -86,7 +87,7 @@ class BnGrad(C.Structure):
 
 EXPORTS = [
     "hdn_last_error", "hdn_version", "hdn_conv_fprop", "hdn_conv_dgrad", "hdn_conv_wgrad",
-    "hdn_conv_tc_supported", "hdn_pool_fwd", "hdn_pool_bwd", "hdn_bn_fold", "hdn_bn_param_grad",
+    "hdn_conv_tc_supported", "hdn_conv_tc_workspace", "hdn_pool_fwd", "hdn_pool_bwd", "hdn_bn_fold", "hdn_bn_param_grad",
     "hdn_bn_bwd_apply", "hdn_dropout_bwd", "hdn_col_stats", "hdn_wce_accum", "hdn_wce_grad",
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
     "hdn_window_accumulate", "hdn_window_finalize", "hdn_dev_malloc", "hdn_dev_free",
@@ -142,6 +143,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.hdn_conv_tc_workspace.argtypes = [C.POINTER(Conv), i32]
+    lib.hdn_conv_tc_workspace.restype = C.c_int64
     _lib = lib
     return lib
 

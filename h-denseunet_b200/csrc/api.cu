@@ -20,6 +20,7 @@ int hdn_conv_wgrad_simt(const hdn_conv* c, float* dw, cudaStream_t st);
 int hdn_colsum(hdn_tensor y, int64_t M, int C, float* out, cudaStream_t st);
 // tcgen05 path (conv_tc.cu)
 int hdn_tc_supported(const hdn_conv* c, int pass);
+long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass);
 int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st);
 int hdn_conv_dgrad_tc(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_t st);
 int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st);
@@ -30,6 +31,11 @@ extern "C" int hdn_version(void) { return 100; }
 extern "C" int hdn_conv_tc_supported(const hdn_conv* c, int pass) {
   if (!c || hdn_validate_conv(c) != HDN_OK) return 0;
   return hdn_tc_supported(c, pass);
+}
+
+extern "C" int64_t hdn_conv_tc_workspace(const hdn_conv* c, int pass) {
+  if (!c || hdn_validate_conv(c) != HDN_OK) return 0;
+  return (int64_t)hdn_tc_workspace_bytes(c, pass);
 }
 
 extern "C" int hdn_conv_fprop(const hdn_conv* c, void* stream) {

@@ -1,6 +1,617 @@
-// tcgen05 implicit-GEMM convolution path (precision == 1).  Placeholder until the kernels land.
+// tcgen05 implicit-GEMM convolution path (precision == 1): bf16 operands, fp32 accumulation in
+// tensor memory.  Covers the stride-1 "same" convolutions of the dense blocks, transitions and
+// decoders: kernels 1x1x1, 1x3x3, 3x3x3 (hybridnet.py:264-298, 11-45, 235-260, 146-176) in
+// fprop and dgrad; everything the reference puts around them (BN -> Scale -> ReLU, ZeroPadding,
+// UpSampling, Add, bias, dropout, batch statistics, ReLU/BN backward sums) is fused into the
+// operand producer or the epilogue.
+//
+// One CTA computes a 128 x BN output tile: 128 GEMM rows = 16 x 8 output pixels of one (n, d)
+// slice (or 128 consecutive positions for 1x1x1), BN <= 256 output channels.
+//
+//   warps 0-3  A producers: load the fp32 input PATCH (tile + halo, 18 x 10 pixels for a 3x3) once
+//              per 64-channel block, apply max(a*x+b, 0) (+ second source, + nearest-neighbour
+//              up-sampling in the index), convert to bf16 and store it in the UMMA no-swizzle
+//              K-major layout: chunk j (8 channels) at j*LBO, pixel q at q*16 bytes.  Every tap of
+//              the filter is then the SAME shared-memory patch read through a descriptor whose
+//              start address is shifted by (th*PW + tw)*16 bytes and whose 8-row-group stride is
+//              PW*16 bytes -- the im2col gather never happens and each input element is loaded
+//              once per tile instead of once per tap.  Afterwards the same warps run the epilogue.
+//   warp 4     weight loader: one elected thread streams pre-packed bf16 weight blocks
+//              (BN x 64, already in core-matrix order) with cp.async.bulk (TMA engine) on mbarriers.
+//   warp 5     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM and
+//              releases stages with tcgen05.commit.
 #include "hdn_common.cuh"
-int hdn_tc_supported(const hdn_conv* c, int pass) { (void)c; (void)pass; return 0; }
-int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st) { (void)c; (void)st; hdn_set_error("tc path not built"); return HDN_ERR_UNSUPPORTED; }
-int hdn_conv_dgrad_tc(const hdn_conv* c, const hdn_dgrad_epi* e, cudaStream_t st) { (void)c; (void)e; (void)st; hdn_set_error("tc path not built"); return HDN_ERR_UNSUPPORTED; }
-int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) { (void)c; (void)dw; (void)st; hdn_set_error("tc path not built"); return HDN_ERR_UNSUPPORTED; }
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int NSA = 3;        // A (activation patch) ring depth
+constexpr int NSB_MAX = 6;    // B (weight block) ring depth upper bound
+
+struct TcParams {
+  int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
+  int kd, kh, kw;
+  int K, NC;                  // contraction channels, output columns
+  int BN, KB, nsb, tmem_cols;
+  int flat;                   // 1: rows are 128 consecutive linear positions (1x1x1, no up-sampling)
+  int PH, PW, P, Ppad;        // patch rows, cols, pixels, padded (odd) pixel count
+  int tiles_w, tiles_h;
+  long long M;
+  int nsrc;
+  hdn_src src[2];             // A operand sources
+  const __nv_bfloat16* wpack;
+  int mode;                   // 0 fprop, 1 dgrad
+  // fprop epilogue
+  const float* bias;
+  hdn_tensor y;
+  double* stat_sum;
+  double* stat_sq;
+  float drop_keep;
+  unsigned long long drop_seed;
+  // dgrad epilogue (one per conv source)
+  int nepi;
+  hdn_src esrc[2];
+  hdn_dgrad_epi epi[2];
+};
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float4 prologue4(float4 x, float4 a, float4 b, int relu) {
+  float4 r;
+  r.x = fmaf(a.x, x.x, b.x); r.y = fmaf(a.y, x.y, b.y); r.z = fmaf(a.z, x.z, b.z); r.w = fmaf(a.w, x.w, b.w);
+  if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+  return r;
+}
+
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t A_BYTES = 8u * p.Ppad * 16u;
+  const uint32_t B_BYTES = (uint32_t)p.BN * 128u;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NSA * A_BYTES;
+  int* pix = reinterpret_cast<int*>(sB + p.nsb * B_BYTES);          // [nsrc][P] in-slab element offsets, -1 = zero
+  float* sstat = reinterpret_cast<float*>(pix + 2 * p.P);           // [4][BN] column partial sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sstat + 4 * p.BN) + 15) & ~uintptr_t(15));
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + NSA;
+  uint64_t* b_full = bars + 2 * NSA;
+  uint64_t* b_empty = bars + 2 * NSA + NSB_MAX;
+  uint64_t* acc_full = bars + 2 * NSA + 2 * NSB_MAX;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  // ---- tile coordinates
+  const int n_tile = blockIdx.y;
+  int n_img = 0, d0 = 0, h0 = 0, w0 = 0;
+  long long m0 = 0;
+  if (p.flat) {
+    m0 = (long long)blockIdx.x * 128;
+  } else {
+    int t = blockIdx.x;
+    const int tw_ = t % p.tiles_w; t /= p.tiles_w;
+    const int th_ = t % p.tiles_h; t /= p.tiles_h;
+    d0 = t % p.D; n_img = t / p.D;
+    h0 = th_ * 16; w0 = tw_ * 8;
+  }
+  const int hh = p.kh >> 1, hw = p.kw >> 1, hd = p.kd >> 1;
+
+  // ---- one-time setup
+  for (int i = tid; i < p.nsrc * p.P; i += TC_THREADS) {
+    const int s = i / p.P, q = i - s * p.P;
+    const hdn_src& S = p.src[s];
+    int off = -1;
+    if (p.flat) {
+      if (m0 + q < p.M) off = q * S.t.ldc;
+    } else {
+      const int vh = h0 - hh + q / p.PW, vw = w0 - hw + q % p.PW;
+      if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
+        const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
+        off = (sh * S.W + sw) * S.t.ldc;
+      }
+    }
+    pix[i] = off;
+  }
+  for (int i = tid; i < 4 * p.BN; i += TC_THREADS) sstat[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < NSA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NSB_MAX; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 5) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps_hw = p.kh * p.kw;
+  const int T = p.kd * taps_hw;
+
+  if (warp < 4) {
+    // =================================================================== A producers
+    const int l8 = lane & 7, pg = lane >> 3;
+    const bool even = (l8 & 1) == 0;
+    const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
+    int sa = 0;
+    uint32_t pha = 0;
+    for (int kb = 0; kb < p.KB; ++kb) {
+      const int c0 = kb * 64;
+      const int cA = c0 + l8 * 4, cB = c0 + 32 + l8 * 4;       // this lane's two channel quads
+      const bool okA = cA < p.K, okB = cB < p.K;               // K % 8 == 0, so a quad is all-in or all-out
+      float4 a0[2], b0[2], a1[2], b1[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
+        b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < p.nsrc) {
+          const hdn_src& S = p.src[s];
+          if (S.pa) { if (okA) a0[s] = ldg4(S.pa + cA); if (okB) a1[s] = ldg4(S.pa + cB); }
+          if (S.pb) { if (okA) b0[s] = ldg4(S.pb + cA); if (okB) b1[s] = ldg4(S.pb + cB); }
+        }
+      }
+      for (int dz = 0; dz < p.kd; ++dz) {
+        const int vd = d0 - hd + dz;
+        if (vd < 0 || vd >= p.D) continue;
+        const float* base[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          base[s] = nullptr;
+          if (s < p.nsrc) {
+            const hdn_src& S = p.src[s];
+            if (p.flat) {
+              base[s] = S.t.p + m0 * S.t.ldc + S.t.coff;
+            } else {
+              const int sd = (S.ud == 2) ? (vd >> 1) : vd;
+              base[s] = S.t.p + ((long long)n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+            }
+          }
+        }
+        tc::mbar_wait(&a_empty[sa], pha ^ 1);
+        uint8_t* dst = sA + sa * A_BYTES;
+        for (int q0 = warp * 4; q0 < p.P; q0 += 16) {
+          const int q = q0 + pg;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          if (q < p.P) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              if (s < p.nsrc) {
+                const int off = pix[s * p.P + q];
+                if (off >= 0) {
+                  const float* g = base[s] + off;
+                  const int relu = p.src[s].relu;
+                  if (okA) { float4 t = prologue4(ldg4(g + cA), a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
+                  if (okB) { float4 t = prologue4(ldg4(g + cB), a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
+                }
+              }
+            }
+          }
+          // lanes (2i, 2i+1) hold channels [8i,8i+4) / [8i+4,8i+8) and [32+8i,..): regroup into 8-channel chunks
+          const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
+          const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+          const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
+          const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+          uint4 o;
+          if (even) { o.x = p00; o.y = p01; o.z = r0; o.w = r1; }     // chunk i      = [own quad A | partner quad A]
+          else      { o.x = r0; o.y = r1; o.z = p10; o.w = p11; }     // chunk 4 + i  = [partner quad B | own quad B]
+          if (q < p.P) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * p.Ppad * 16u + (uint32_t)q * 16u) = o;
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&a_full[sa]);
+        if (++sa == NSA) { sa = 0; pha ^= 1; }
+      }
+    }
+
+    // =================================================================== epilogue
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int hr = row >> 3, wr = row & 7;
+    bool rvalid;
+    long long m;
+    int oh = 0, ow = 0;
+    if (p.flat) {
+      m = m0 + row;
+      rvalid = m < p.M;
+    } else {
+      oh = h0 + hr; ow = w0 + wr;
+      rvalid = oh < p.H && ow < p.W;
+      m = (((long long)n_img * p.D + d0) * p.H + oh) * p.W + ow;
+    }
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float v[16];
+
+    if (p.mode == 0) {
+      const bool do_stats = p.stat_sum != nullptr;
+      const bool vec = (p.NC % 4 == 0) && (p.y.ldc % 4 == 0) && (p.y.coff % 4 == 0);
+      float* yrow = const_cast<float*>(p.y.p) + m * p.y.ldc + p.y.coff;
+      for (int cc = 0; cc < p.BN; cc += 16) {
+        tc::tmem_ld16(taddr + cc, v);
+        const int col0 = n_tile * p.BN + cc;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int col = col0 + i;
+          float t = v[i];
+          if (col < p.NC) {
+            if (p.bias) t += __ldg(p.bias + col);
+            if (p.drop_keep < 1.0f) t *= hdn_drop_scale(p.drop_seed, (uint64_t)m * p.NC + col, p.drop_keep);
+          }
+          v[i] = t;
+        }
+        if (rvalid) {
+          if (vec) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (col0 + i < p.NC) *reinterpret_cast<float4*>(yrow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (col0 + i < p.NC) yrow[col0 + i] = v[i];
+          }
+        }
+        if (do_stats) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float s = rvalid ? v[i] : 0.f;
+            float q2 = s * s;
+            s = warp_sum(s); q2 = warp_sum(q2);
+            if (lane == i) { atomicAdd(&sstat[cc + i], s); atomicAdd(&sstat[p.BN + cc + i], q2); }
+          }
+        }
+      }
+      if (do_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = tid; c < p.BN; c += 128) {
+          const int col = n_tile * p.BN + c;
+          if (col < p.NC) {
+            atomicAdd(p.stat_sum + col, (double)sstat[c]);
+            atomicAdd(p.stat_sq + col, (double)sstat[p.BN + c]);
+          }
+        }
+      }
+    } else {
+      // dgrad: v = dz at a (virtual-resolution) input position; per source: reduce the up-sampling
+      // sub-positions, ReLU mask from the stored value, S1/S2 sums, then dx (+)= a*du or du (+)= du.
+      for (int cc = 0; cc < p.BN; cc += 16) {
+        tc::tmem_ld16(taddr + cc, v);
+        const int col0 = n_tile * p.BN + cc;
+        for (int e = 0; e < p.nepi; ++e) {
+          const hdn_dgrad_epi& E = p.epi[e];
+          if (E.mode == 2) continue;
+          const hdn_src& S = p.esrc[e];
+          long long ms = m;
+          bool writer = rvalid;
+          if (!p.flat) {
+            const int sd = (S.ud == 2) ? (d0 >> 1) : d0, sh = (S.uh == 2) ? (oh >> 1) : oh, sw = (S.uw == 2) ? (ow >> 1) : ow;
+            ms = (((long long)n_img * S.D + sd) * S.H + sh) * S.W + sw;
+            if (S.uw == 2 && (wr & 1)) writer = false;
+            if (S.uh == 2 && (hr & 1)) writer = false;
+          }
+          const bool atom = (S.ud == 2);
+          const float* xrow = S.t.p + ms * S.t.ldc + S.t.coff;
+          const bool do_s = E.s1 != nullptr;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float dz[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float t = rvalid ? v[i + j] : 0.f;
+              if (S.uw == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
+              if (S.uh == 2) t += __shfl_xor_sync(0xffffffffu, t, 8);
+              dz[j] = t;
+            }
+            const int col = col0 + i;
+            const bool cok = col < p.NC;          // NC % 4 == 0 on this path
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), a = make_float4(1.f, 1.f, 1.f, 1.f), b = x, ctr = x;
+            if (cok) {
+              if (writer) x = ldg4(xrow + col);
+              if (S.pa) a = ldg4(S.pa + col);
+              if (S.pb) b = ldg4(S.pb + col);
+              if (do_s && E.center) ctr = ldg4(E.center + col);
+            }
+            const float xa[4] = {x.x, x.y, x.z, x.w}, aa[4] = {a.x, a.y, a.z, a.w}, ba[4] = {b.x, b.y, b.z, b.w},
+                        ca[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+            float du[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float t = (writer && cok) ? dz[j] : 0.f;
+              if (S.relu && !(fmaf(aa[j], xa[j], ba[j]) > 0.f)) t = 0.f;
+              du[j] = t;
+            }
+            if (do_s) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float s1 = warp_sum(du[j]);
+                float s2 = warp_sum(du[j] * (xa[j] - ca[j]));
+                if (lane == i + j) { atomicAdd(&sstat[(2 * e) * p.BN + cc + i + j], s1); atomicAdd(&sstat[(2 * e + 1) * p.BN + cc + i + j], s2); }
+              }
+            }
+            if (writer && cok) {
+              if (E.mode == 0) {
+                float* q = const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff + col;
+                float4 g = make_float4(aa[0] * du[0], aa[1] * du[1], aa[2] * du[2], aa[3] * du[3]);
+                if (atom) { atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w); }
+                else {
+                  if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+                  *reinterpret_cast<float4*>(q) = g;
+                }
+              } else {
+                float* q = E.du + ms * p.NC + col;
+                float4 g = make_float4(du[0], du[1], du[2], du[3]);
+                if (atom) { atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w); }
+                else {
+                  if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+                  *reinterpret_cast<float4*>(q) = g;
+                }
+              }
+            }
+          }
+        }
+      }
+      bool any_s = false;
+      for (int e = 0; e < p.nepi; ++e) any_s = any_s || (p.epi[e].mode != 2 && p.epi[e].s1 != nullptr);
+      if (any_s) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int e = 0; e < p.nepi; ++e) {
+          const hdn_dgrad_epi& E = p.epi[e];
+          if (E.mode == 2 || E.s1 == nullptr) continue;
+          for (int c = tid; c < p.BN; c += 128) {
+            const int col = n_tile * p.BN + c;
+            if (col < p.NC) {
+              const float s1 = sstat[(2 * e) * p.BN + c], s2 = sstat[(2 * e + 1) * p.BN + c];
+              if (s1 != 0.f) atomicAdd(E.s1 + col, (double)s1);
+              if (s2 != 0.f) atomicAdd(E.s2 + col, (double)s2);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // =================================================================== weight loader (TMA engine)
+    if (lane == 0) {
+      const __nv_bfloat16* wp = p.wpack + (size_t)n_tile * p.KB * T * ((size_t)p.BN * 64);
+      int sb = 0;
+      uint32_t phb = 0;
+      for (int kb = 0; kb < p.KB; ++kb)
+        for (int dz = 0; dz < p.kd; ++dz) {
+          const int vd = d0 - hd + dz;
+          if (vd < 0 || vd >= p.D) continue;
+          for (int t2 = 0; t2 < taps_hw; ++t2) {
+            const int tap = dz * taps_hw + t2;
+            tc::mbar_wait(&b_empty[sb], phb ^ 1);
+            tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+            tc::bulk_g2s(sB + sb * B_BYTES, wp + ((size_t)kb * T + tap) * ((size_t)p.BN * 64), B_BYTES, &b_full[sb]);
+            if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+          }
+        }
+    }
+  } else {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 0, 0);
+      const uint32_t lbo_a = (uint32_t)p.Ppad * 16u, sbo_a = (uint32_t)p.PW * 16u;
+      const uint32_t lbo_b = (uint32_t)p.BN * 16u, sbo_b = 128u;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0, acc = 0;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int cv = min(64, p.K - kb * 64);
+        const int nk = (cv + 15) >> 4;
+        for (int dz = 0; dz < p.kd; ++dz) {
+          const int vd = d0 - hd + dz;
+          if (vd < 0 || vd >= p.D) continue;
+          tc::mbar_wait(&a_full[sa], pha);
+          tc::tc_fence_after();
+          const uint32_t a_stage = tc::smem_u32(sA + sa * A_BYTES);
+          for (int t2 = 0; t2 < taps_hw; ++t2) {
+            const int th = t2 / p.kw, tw = t2 - th * p.kw;
+            tc::mbar_wait(&b_full[sb], phb);
+            tc::tc_fence_after();
+            const uint32_t a_base = a_stage + (uint32_t)(th * p.PW + tw) * 16u;
+            const uint32_t b_base = tc::smem_u32(sB + sb * B_BYTES);
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t ad = tc::make_smem_desc(a_base + (uint32_t)k * 2u * lbo_a, lbo_a, sbo_a);
+              const uint64_t bd = tc::make_smem_desc(b_base + (uint32_t)k * 2u * lbo_b, lbo_b, sbo_b);
+              tc::umma_bf16(tmem_base, ad, bd, idesc, acc);
+              acc = 1;
+            }
+            tc::umma_commit(&b_empty[sb]);
+            if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+          }
+          tc::umma_commit(&a_empty[sa]);
+          if (++sa == NSA) { sa = 0; pha ^= 1; }
+        }
+      }
+      tc::umma_commit(acc_full);
+    }
+  }
+
+  // ---- teardown
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+// out[n_tile][kb][tap][chunk j][n][8]  (bf16)  =  B[n = column][k = kb*64 + j*8 + e]
+//   role 0 (fprop): B[n][k] = w[tap][k][n]                       K = Cin,  NC = Cout
+//   role 1 (dgrad): B[n][k] = w[flip(tap)][n][k]                 K = Cout, NC = Cin
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                           int Cin, int Cout, int kd, int kh, int kw, int BN, int KB,
+                                                           int n_tiles, int role, long long total) {
+  const int T = kd * kh * kw;
+  const int K = role == 0 ? Cin : Cout, NC = role == 0 ? Cout : Cin;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    long long t = idx;
+    const int e = (int)(t % 8); t /= 8;
+    const int n = (int)(t % BN); t /= BN;
+    const int j = (int)(t % 8); t /= 8;
+    const int tap = (int)(t % T); t /= T;
+    const int kb = (int)(t % KB); t /= KB;
+    const int nt = (int)t;
+    const int k = kb * 64 + j * 8 + e, col = nt * BN + n;
+    float v = 0.f;
+    if (k < K && col < NC) {
+      if (role == 0) v = __ldg(w + ((long long)tap * Cin + k) * Cout + col);
+      else v = __ldg(w + ((long long)(T - 1 - tap) * Cin + col) * Cout + k);
+    }
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) zero_window_kernel(hdn_tensor t, long long M, int C) {
+  const long long total = M * C;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long m = i / C;
+    const int c = (int)(i - m * C);
+    const_cast<float*>(t.p)[m * t.ldc + t.coff + c] = 0.f;
+  }
+}
+
+struct TcPlan {
+  int BN, n_tiles, KB, nsb, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
+  long long ws_elems;
+  size_t smem;
+};
+
+bool tc_shape_ok(const hdn_conv* c) {
+  if (c->sd != 1 || c->sh != 1 || c->sw != 1) return false;
+  const bool k111 = c->kd == 1 && c->kh == 1 && c->kw == 1;
+  const bool k133 = c->kd == 1 && c->kh == 3 && c->kw == 3;
+  const bool k333 = c->kd == 3 && c->kh == 3 && c->kw == 3;
+  if (!(k111 || k133 || k333)) return false;
+  if (c->pd != c->kd / 2 || c->ph != c->kh / 2 || c->pw != c->kw / 2) return false;
+  const hdn_src& s0 = c->src[0];
+  if (c->D != s0.D * s0.ud || c->H != s0.H * s0.uh || c->W != s0.W * s0.uw) return false;
+  for (int i = 0; i < c->nsrc; ++i) {
+    const hdn_src& s = c->src[i];
+    if (s.t.ldc % 4 || s.t.coff % 4) return false;
+    if ((reinterpret_cast<uintptr_t>(s.t.p) & 15) != 0) return false;
+  }
+  if (c->y.ldc % 4 || c->y.coff % 4 || (reinterpret_cast<uintptr_t>(c->y.p) & 15) != 0) return false;
+  return true;
+}
+
+TcPlan tc_plan(const hdn_conv* c, int K, int NC) {
+  TcPlan pl;
+  pl.n_tiles = (NC + 255) / 256;
+  int bn = (NC + pl.n_tiles - 1) / pl.n_tiles;
+  pl.BN = (bn + 15) / 16 * 16;
+  pl.KB = (K + 63) / 64;
+  const hdn_src& s0 = c->src[0];
+  bool up = false;
+  for (int i = 0; i < c->nsrc; ++i) up = up || c->src[i].ud != 1 || c->src[i].uh != 1 || c->src[i].uw != 1;
+  pl.flat = (c->kd == 1 && c->kh == 1 && c->kw == 1 && !up) ? 1 : 0;
+  (void)s0;
+  pl.PH = 16 + c->kh - 1;
+  pl.PW = 8 + c->kw - 1;
+  pl.P = pl.PH * pl.PW;
+  pl.Ppad = pl.P | 1;
+  pl.tiles_h = (c->H + 15) / 16;
+  pl.tiles_w = (c->W + 7) / 8;
+  const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * 128;
+  int nsb = (int)((96 * 1024) / b_bytes);
+  pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
+  int cols = 32;
+  while (cols < pl.BN) cols *= 2;
+  pl.tmem_cols = cols;
+  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (c->kd * c->kh * c->kw) * pl.BN * 64;
+  pl.smem = NSA * a_bytes + pl.nsb * b_bytes + 2ull * pl.P * 4 + 4ull * pl.BN * 4 + 16 + (2 * NSA + 2 * NSB_MAX + 1) * 8 + 16;
+  return pl;
+}
+
+int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_t st) {
+  const int K = mode == 0 ? c->Cin : c->Cout, NC = mode == 0 ? c->Cout : c->Cin;
+  const TcPlan pl = tc_plan(c, K, NC);
+  HDN_CHECK_ARG(c->ws != nullptr && c->ws_bytes >= pl.ws_elems * 2, "conv tc: workspace too small (%lld < %lld bytes)",
+                (long long)c->ws_bytes, (long long)pl.ws_elems * 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { hdn_set_error("conv tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
+    attr_set = true;
+  }
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(c->ws);
+  {
+    long long total = pl.ws_elems;
+    unsigned g = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    pack_weights_kernel<<<g, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.n_tiles, mode, total);
+    HDN_CHECK_LAUNCH("pack_weights");
+  }
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = c->N; p.D = c->D; p.H = c->H; p.W = c->W;
+  p.kd = c->kd; p.kh = c->kh; p.kw = c->kw;
+  p.K = K; p.NC = NC;
+  p.BN = pl.BN; p.KB = pl.KB; p.nsb = pl.nsb; p.tmem_cols = pl.tmem_cols;
+  p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
+  p.M = (long long)c->N * c->D * c->H * c->W;
+  p.wpack = wp;
+  p.mode = mode;
+  if (mode == 0) {
+    p.nsrc = c->nsrc;
+    p.src[0] = c->src[0];
+    p.src[1] = c->src[1];
+    p.bias = c->bias; p.y = c->y; p.stat_sum = c->stat_sum; p.stat_sq = c->stat_sq;
+    p.drop_keep = c->drop_keep; p.drop_seed = c->drop_seed;
+  } else {
+    // the A operand is dY on the output grid, taken as is
+    p.nsrc = 1;
+    hdn_src dy;
+    memset(&dy, 0, sizeof(dy));
+    dy.t = c->y; dy.D = c->D; dy.H = c->H; dy.W = c->W; dy.ud = dy.uh = dy.uw = 1;
+    p.src[0] = dy;
+    p.nepi = c->nsrc;
+    for (int i = 0; i < c->nsrc; ++i) {
+      p.esrc[i] = c->src[i];
+      p.epi[i] = epi[i];
+      if (epi[i].mode == 2) continue;
+      const hdn_src& s = c->src[i];
+      HDN_CHECK_ARG(epi[i].mode != 0 || (epi[i].dx.ldc % 4 == 0 && epi[i].dx.coff % 4 == 0), "conv_dgrad tc: dx window not 16-byte aligned");
+      if (s.ud == 2 && !epi[i].accumulate) {
+        // depth sub-positions live in different CTAs and are combined with atomics: start from zero
+        const long long Ms = (long long)c->N * s.D * s.H * s.W;
+        if (epi[i].mode == 0) {
+          unsigned g = (unsigned)((Ms * c->Cin + 255) / 256 > 148 * 16 ? 148 * 16 : (Ms * c->Cin + 255) / 256);
+          zero_window_kernel<<<g, 256, 0, st>>>(epi[i].dx, Ms, c->Cin);
+          HDN_CHECK_LAUNCH("zero_window");
+        } else {
+          cudaError_t e = cudaMemsetAsync(epi[i].du, 0, (size_t)Ms * c->Cin * sizeof(float), st);
+          if (e != cudaSuccess) { hdn_set_error("conv_dgrad tc: memset: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
+        }
+      }
+    }
+  }
+  const long long tiles = pl.flat ? (p.M + 127) / 128 : (long long)c->N * c->D * pl.tiles_h * pl.tiles_w;
+  HDN_CHECK_ARG(tiles < (1ll << 31), "conv tc: too many tiles");
+  dim3 grid((unsigned)tiles, (unsigned)pl.n_tiles);
+  conv_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p);
+  HDN_CHECK_LAUNCH(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
+  return HDN_OK;
+}
+
+}  // namespace
+
+int hdn_tc_supported(const hdn_conv* c, int pass) {
+  if (!tc_shape_ok(c)) return 0;
+  if (pass == 0) return (c->Cin % 8 == 0) ? 1 : 0;
+  if (pass == 1) return (c->Cout % 8 == 0 && c->Cin % 8 == 0) ? 1 : 0;
+  return 0;   // wgrad: not yet on the tensor-core path
+}
+
+long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
+  if (!hdn_tc_supported(c, pass)) return 0;
+  const int K = pass == 0 ? c->Cin : c->Cout, NC = pass == 0 ? c->Cout : c->Cin;
+  return tc_plan(c, K, NC).ws_elems * 2;
+}
+
+int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st) { return tc_launch(c, nullptr, 0, st); }
+int hdn_conv_dgrad_tc(const hdn_conv* c, const hdn_dgrad_epi* e, cudaStream_t st) { return tc_launch(c, e, 1, st); }
+int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
+  (void)c; (void)dw; (void)st;
+  hdn_set_error("conv_wgrad: tensor-core path not built");
+  return HDN_ERR_UNSUPPORTED;
+}

@@ -180,6 +180,9 @@ class CudaBackend(object):
                 c.stat_sq = d.stat[1].data_ptr()
             c.drop_keep, c.drop_seed, c.precision = d.drop_keep, d.drop_seed, d.precision
             d.__dict__[key] = c
+        ws = getattr(d, "ws", None)
+        if ws is not None and c.ws != ws.data_ptr():
+            c.ws, c.ws_bytes = ws.data_ptr(), ws.numel() * ws.element_size()
         return c
 
     def _epi(self, e, Cin):
@@ -199,6 +202,9 @@ class CudaBackend(object):
     # -- ops
     def conv_tc_supported(self, d, which):
         return bool(self.lib.hdn_conv_tc_supported(C.byref(self._conv(d)), which))
+
+    def conv_tc_workspace(self, d, which):
+        return int(self.lib.hdn_conv_tc_workspace(C.byref(self._conv(d)), which))
 
     def conv_fprop(self, d):
         _lib.check(self._run(self._conv_key(d, "fprop"), self._conv_flops(d), 1, self.lib.hdn_conv_fprop,
@@ -512,20 +518,21 @@ class ConvOp(object):
                              drop_keep=1.0 - self.drop_rate, drop_seed=0, precision=0)
         self.prec = [0, 0, 0]
         if net.precision == "bf16":
+            self.desc.precision = 1
             for i in range(3):
-                self.desc.precision = 1
                 self.prec[i] = 1 if net.be.conv_tc_supported(self.desc, i) else 0
+                if self.prec[i]:
+                    net.ws_need = max(net.ws_need, net.be.conv_tc_workspace(self.desc, i))
             self.desc.precision = 0
         net.report.append((self.name, tuple(self.prec)))
 
     def _set_prec(self, which):
         d = self.desc
-        if d.precision != self.prec[which]:
-            d.precision = self.prec[which]
-            for key in ("_c_f", "_c_g"):
-                c = d.__dict__.get(key)
-                if c is not None:
-                    c.precision = d.precision
+        d.precision = self.prec[which]
+        for key in ("_c_f", "_c_g"):
+            c = d.__dict__.get(key)
+            if c is not None and c.precision != d.precision:
+                c.precision = d.precision
 
     def forward(self):
         d = self.desc
@@ -750,6 +757,8 @@ class Net(object):
         self.inputs = {}
         self.outputs = {}
         self.loss = None
+        self.ws_need = 0
+        self.ws = None
 
     # -- graph construction
     def buffer(self, name, N, D, H, W, C_):
@@ -846,6 +855,12 @@ class Net(object):
         for op in self.ops:
             if not isinstance(op, Fold):
                 op.compile()
+        if self.ws_need:
+            # one scratch for the packed bf16 weights of whichever convolution is running (stream-ordered reuse)
+            self.ws = torch.empty(self.ws_need, dtype=torch.uint8, device=self.device)
+            for op in self.ops:
+                if isinstance(op, ConvOp):
+                    op.desc.ws = self.ws
         if self.training and self.loss is not None:
             planner = Planner(self)
             for op in reversed(self.ops):

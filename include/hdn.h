@@ -72,6 +72,8 @@ typedef struct {
   float drop_keep;        /* 1.0 => no dropout; else y = y*mask/keep (KB:2888) */
   uint64_t drop_seed;
   int precision;          /* 0: fp32 FMA (parity path)  1: tcgen05 bf16 operands, fp32 accumulate */
+  void* ws;               /* precision 1: device scratch for the packed bf16 weight blocks of this call */
+  int64_t ws_bytes;       /*   >= hdn_conv_tc_workspace(c, pass); may be shared by all calls of one stream */
 } hdn_conv;
 
 /* Epilogue of a data-gradient: given dz = dL/d(prologue output) it forms
@@ -98,6 +100,8 @@ int hdn_conv_dgrad(const hdn_conv* c, const hdn_dgrad_epi* epi, void* stream);
 int hdn_conv_wgrad(const hdn_conv* c, float* dw, float* dbias, void* stream);
 /* 1 if the tcgen05 path (precision == 1) takes this descriptor for the given pass, else 0. */
 int hdn_conv_tc_supported(const hdn_conv* c, int pass /*0 fprop 1 dgrad 2 wgrad*/);
+/* Bytes of hdn_conv.ws the tcgen05 path needs for this descriptor and pass (0 if unsupported). */
+int64_t hdn_conv_tc_workspace(const hdn_conv* c, int pass);
 
 /* Pooling (KB:3354-3432).  kind 0: max 3x3(x3)/2 after zero-pad 1 (the ZeroPadding + VALID
  * max-pool of hybridnet.py:128-129,215-216; input passes through the src prologue first);

@@ -43,14 +43,14 @@ def _oracle_2d(w0, x, y, skip):
 
 @pytest.mark.parametrize("skip", [False, True])
 def test_unet2d_train_step_fp32(cuda_dev, skip):
-    a = Args(b=2, input_size=64)
+    a = Args(b=2, input_size=128)      # block 5 is 4x4: smaller makes training-mode BN statistics degenerate
     m = hdn.DenseUNet(reduction=0.5, args=a, skip=skip, precision="fp32")
     m.dropout = False
     perturb_params(m)
     m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy_2ddense])
     rng = np.random.default_rng(0)
-    x = rng.normal(0, 60, (2, 64, 64, 3)).astype(np.float32)
-    y = rng.integers(0, 3, (2, 64, 64, 1)).astype(np.int16)
+    x = rng.normal(0, 60, (2, 128, 128, 3)).astype(np.float32)
+    y = rng.integers(0, 3, (2, 128, 128, 1)).astype(np.int16)
     w0 = m.get_weights_dict()
     o = _oracle_2d(w0, x, y, skip)
     loss = m.train_on_batch(x, y)

@@ -28,6 +28,7 @@ namespace {
 constexpr int TC_THREADS = 192;
 constexpr int NSA = 3;        // A (activation patch) ring depth
 constexpr int NSB_MAX = 6;    // B (weight block) ring depth upper bound
+constexpr int UB = 4;         // producer: pixel groups loaded ahead per warp
 
 struct TcParams {
   int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
@@ -169,32 +170,52 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
         }
         tc::mbar_wait(&a_empty[sa], pha ^ 1);
         uint8_t* dst = sA + sa * A_BYTES;
-        for (int q0 = warp * 4; q0 < p.P; q0 += 16) {
-          const int q = q0 + pg;
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (q < p.P) {
+        // UB pixel groups per warp are loaded before any is used: the loads of a batch are all in flight
+        // together (memory-level parallelism is what bounds this producer, not instruction count)
+        for (int q0 = warp * 4; q0 < p.P; q0 += 16 * UB) {
+          float4 r0[UB][2], r1[UB][2];
+          bool inb[UB][2];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int q = q0 + u * 16 + pg;
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
-              if (s < p.nsrc) {
+              inb[u][s] = false;
+              r0[u][s] = r1[u][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (s < p.nsrc && q < p.P) {
                 const int off = pix[s * p.P + q];
                 if (off >= 0) {
+                  inb[u][s] = true;
                   const float* g = base[s] + off;
-                  const int relu = p.src[s].relu;
-                  if (okA) { float4 t = prologue4(ldg4(g + cA), a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
-                  if (okB) { float4 t = prologue4(ldg4(g + cB), a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
+                  if (okA) r0[u][s] = ldg4(g + cA);
+                  if (okB) r1[u][s] = ldg4(g + cB);
                 }
               }
             }
           }
-          // lanes (2i, 2i+1) hold channels [8i,8i+4) / [8i+4,8i+8) and [32+8i,..): regroup into 8-channel chunks
-          const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
-          const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
-          const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
-          const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-          uint4 o;
-          if (even) { o.x = p00; o.y = p01; o.z = r0; o.w = r1; }     // chunk i      = [own quad A | partner quad A]
-          else      { o.x = r0; o.y = r1; o.z = p10; o.w = p11; }     // chunk 4 + i  = [partner quad B | own quad B]
-          if (q < p.P) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * p.Ppad * 16u + (uint32_t)q * 16u) = o;
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            if (q0 + u * 16 >= p.P) break;                       // warp-uniform
+            const int q = q0 + u * 16 + pg;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              if (s < p.nsrc && inb[u][s]) {                     // zero padding is applied AFTER BN/Scale/ReLU
+                const int relu = p.src[s].relu;
+                if (okA) { float4 t = prologue4(r0[u][s], a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
+                if (okB) { float4 t = prologue4(r1[u][s], a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
+              }
+            }
+            // lanes (2i, 2i+1) hold channels [8i,8i+4) / [8i+4,8i+8) and [32+8i,..): regroup into 8-channel chunks
+            const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
+            const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+            const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
+            const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+            uint4 o;
+            if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }     // chunk i      = [own quad A | partner quad A]
+            else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }     // chunk 4 + i  = [partner quad B | own quad B]
+            if (q < p.P) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * p.Ppad * 16u + (uint32_t)q * 16u) = o;
+          }
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[sa]);
@@ -223,7 +244,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
     if (p.mode == 0) {
       const bool do_stats = p.stat_sum != nullptr;
-      const bool vec = (p.NC % 4 == 0) && (p.y.ldc % 4 == 0) && (p.y.coff % 4 == 0);
+      const bool vec = (p.NC % 4 == 0) && (p.y.ldc % 4 == 0) && (p.y.coff % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0);
       float* yrow = const_cast<float*>(p.y.p) + m * p.y.ldc + p.y.coff;
       for (int cc = 0; cc < p.BN; cc += 16) {
         tc::tmem_ld16(taddr + cc, v);
@@ -440,24 +462,36 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 //   role 1 (dgrad): B[n][k] = w[flip(tap)][n][k]                 K = Cout, NC = Cin
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int Cin, int Cout, int kd, int kh, int kw, int BN, int KB,
-                                                           int n_tiles, int role, long long total) {
+                                                           int n_tiles, int role, long long total16) {
+  // one thread per 16-byte output unit (n, chunk j): 8 consecutive k.  role 0 reads w[tap][k][col] (threads
+  // adjacent in n -> coalesced over col); role 1 reads w[tap'][col][k..k+8) (two float4 per thread).
   const int T = kd * kh * kw;
   const int K = role == 0 ? Cin : Cout, NC = role == 0 ? Cout : Cin;
-  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total16; idx += (long long)gridDim.x * 256) {
     long long t = idx;
-    const int e = (int)(t % 8); t /= 8;
     const int n = (int)(t % BN); t /= BN;
     const int j = (int)(t % 8); t /= 8;
     const int tap = (int)(t % T); t /= T;
     const int kb = (int)(t % KB); t /= KB;
     const int nt = (int)t;
-    const int k = kb * 64 + j * 8 + e, col = nt * BN + n;
-    float v = 0.f;
-    if (k < K && col < NC) {
-      if (role == 0) v = __ldg(w + ((long long)tap * Cin + k) * Cout + col);
-      else v = __ldg(w + ((long long)(T - 1 - tap) * Cin + col) * Cout + k);
+    const int k0 = kb * 64 + j * 8, col = nt * BN + n;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (col < NC && k0 < K) {          // K % 8 == 0: a chunk is all-in or all-out
+      if (role == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(w + ((long long)tap * Cin + k0 + e) * Cout + col);
+      } else {
+        const float* src = w + ((long long)(T - 1 - tap) * Cin + col) * Cout + k0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e);
+      }
     }
-    out[idx] = __float2bfloat16_rn(v);
+    uint4 o;
+    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
+    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[idx] = o;
   }
 }
 
@@ -490,8 +524,10 @@ bool tc_shape_ok(const hdn_conv* c) {
     if (s.t.ldc % 4 || s.t.coff % 4) return false;
     if ((reinterpret_cast<uintptr_t>(s.t.p) & 15) != 0) return false;
   }
-  if (c->y.ldc % 4 || c->y.coff % 4 || (reinterpret_cast<uintptr_t>(c->y.p) & 15) != 0) return false;
   return true;
+}
+bool tc_y_aligned(const hdn_conv* c) {
+  return c->y.ldc % 4 == 0 && c->y.coff % 4 == 0 && (reinterpret_cast<uintptr_t>(c->y.p) & 15) == 0;
 }
 
 TcPlan tc_plan(const hdn_conv* c, int K, int NC) {
@@ -535,7 +571,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   }
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(c->ws);
   {
-    long long total = pl.ws_elems;
+    long long total = pl.ws_elems / 8;
     unsigned g = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     pack_weights_kernel<<<g, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.n_tiles, mode, total);
     HDN_CHECK_LAUNCH("pack_weights");
@@ -595,23 +631,20 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
 
 }  // namespace
 
+int hdn_wgrad_tc_supported(const hdn_conv* c);
+
 int hdn_tc_supported(const hdn_conv* c, int pass) {
   if (!tc_shape_ok(c)) return 0;
   if (pass == 0) return (c->Cin % 8 == 0) ? 1 : 0;
-  if (pass == 1) return (c->Cout % 8 == 0 && c->Cin % 8 == 0) ? 1 : 0;
-  return 0;   // wgrad: not yet on the tensor-core path
+  if (pass == 1) return (c->Cout % 8 == 0 && c->Cin % 8 == 0 && tc_y_aligned(c)) ? 1 : 0;   // dY is the A operand
+  return hdn_wgrad_tc_supported(c);
 }
 
 long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
-  if (!hdn_tc_supported(c, pass)) return 0;
+  if (!hdn_tc_supported(c, pass) || pass == 2) return 0;
   const int K = pass == 0 ? c->Cin : c->Cout, NC = pass == 0 ? c->Cout : c->Cin;
   return tc_plan(c, K, NC).ws_elems * 2;
 }
 
 int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st) { return tc_launch(c, nullptr, 0, st); }
 int hdn_conv_dgrad_tc(const hdn_conv* c, const hdn_dgrad_epi* e, cudaStream_t st) { return tc_launch(c, e, 1, st); }
-int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
-  (void)c; (void)dw; (void)st;
-  hdn_set_error("conv_wgrad: tensor-core path not built");
-  return HDN_ERR_UNSUPPORTED;
-}

@@ -1,0 +1,419 @@
+// tcgen05 weight-gradient kernel (precision == 1):  dW[tap][ci][co] += sum_pos A[pos + off(tap)][ci] * dY[pos][co]
+// for the stride-1 "same" convolutions (1x1x1, 1x3x3, 3x3x3), A being the convolution's (virtual) input
+// max(a*x+b,0) (+ second source, up-sampling folded into the index) exactly as in fprop.
+//
+// GEMM view per tap: D[ci (M=128)][co (N=BN)] += At[ci][pos] * dY[pos][co], contraction over positions.
+// Both operands are "MN-major" (channels contiguous), which is how NDHWC activations already lie in
+// memory, so the producers use the same chunk layout as fprop: 8-channel chunk j at j*SBO, pixel q at
+// q*16 bytes.  One position tile = 16 x 8 pixels; its input PATCH (tile + halo) is staged once and every
+// tap of the tap group reads it through a shifted descriptor; each tap owns BN TMEM columns.
+// A CTA owns (128 input channels) x (BN output channels) x (tap group) and loops over its share of
+// the position tiles (split-K over CTAs); the epilogue adds the fp32 accumulators into dW with
+// vector reductions (REDG.ADD.F32x4).
+//
+//   warps 0-7  producers (patch + dY tile -> bf16 chunks in shared memory), then epilogue
+//   warp  8    MMA issuer (one elected thread)
+#include "hdn_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int WG_THREADS = 288;
+constexpr int WG_PROD = 256;
+constexpr int NS = 2;          // stage ring depth
+constexpr int WUB = 3;         // pixel groups loaded ahead per producer warp
+
+struct WgParams {
+  int N, D, H, W;              // output grid (= virtual input grid)
+  int kd, kh, kw;
+  int Cin, Cout;
+  int BN, G, groups;           // column tile, taps per group, number of tap groups
+  int ci_tiles, co_tiles;
+  int flat;
+  int PH, PW, P, Ppad;         // patch of ONE tap group (rows PH, cols PW)
+  int row0_mode;               // 0: group covers all kh rows; 1: group g covers kernel row (g % kh) only
+  int tiles_w, tiles_h;
+  long long n_pos_tiles;       // position tiles per slice set
+  long long M;
+  int nsrc;
+  hdn_src src[2];
+  hdn_tensor dy;
+  float* dw;
+  int tmem_cols;
+};
+
+__device__ __forceinline__ float4 ldg4w(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 pro4(float4 x, float4 a, float4 b, int relu) {
+  float4 r;
+  r.x = fmaf(a.x, x.x, b.x); r.y = fmaf(a.y, x.y, b.y); r.z = fmaf(a.z, x.z, b.z); r.w = fmaf(a.w, x.w, b.w);
+  if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+  return r;
+}
+
+// Stage one 64-channel block [cbase, cbase+64) of `npx` pixels into chunk layout at dst (8 chunks, stride
+// ppad*16 bytes).  offs[s*npx + q] is the element offset of pixel q in source s (or -1 => zeros).
+__device__ __forceinline__ void stage_block(const hdn_src* src, int nsrc, const float* const* base, const int* offs,
+                                            int npx, int ppad, int cbase, int climit, uint8_t* dst, int nchunks,
+                                            int pwarp, int lane) {
+  const int l8 = lane & 7, pg = lane >> 3;
+  const bool even = (l8 & 1) == 0;
+  const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
+  const int cA = cbase + l8 * 4, cB = cbase + 32 + l8 * 4;
+  const bool okA = cA < climit, okB = cB < climit;
+  float4 a0[2], b0[2], a1[2], b1[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
+    b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s < nsrc) {
+      if (src[s].pa) { if (okA) a0[s] = ldg4w(src[s].pa + cA); if (okB) a1[s] = ldg4w(src[s].pa + cB); }
+      if (src[s].pb) { if (okA) b0[s] = ldg4w(src[s].pb + cA); if (okB) b1[s] = ldg4w(src[s].pb + cB); }
+    }
+  }
+  for (int q0 = pwarp * 4; q0 < npx; q0 += 32 * WUB) {
+    float4 r0[WUB][2], r1[WUB][2];
+    bool inb[WUB][2];
+#pragma unroll
+    for (int u = 0; u < WUB; ++u) {
+      const int q = q0 + u * 32 + pg;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        inb[u][s] = false;
+        r0[u][s] = r1[u][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s < nsrc && q < npx) {
+          const int off = offs[s * npx + q];
+          if (off >= 0) {
+            inb[u][s] = true;
+            const float* g = base[s] + off;
+            if (okA) r0[u][s] = ldg4w(g + cA);
+            if (okB) r1[u][s] = ldg4w(g + cB);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < WUB; ++u) {
+      if (q0 + u * 32 >= npx) break;
+      const int q = q0 + u * 32 + pg;
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (s < nsrc && inb[u][s]) {
+          const int relu = src[s].relu;
+          if (okA) { float4 t = pro4(r0[u][s], a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
+          if (okB) { float4 t = pro4(r1[u][s], a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
+        }
+      }
+      const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
+      const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+      const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
+      const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+      uint4 o;
+      if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }
+      else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }
+      if (q < npx && chunk < nchunks) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t A_BYTES = 16u * p.Ppad * 16u;                       // 128 channels of the patch
+  const uint32_t B_BYTES = (uint32_t)((p.BN + 7) / 8) * 129u * 16u;  // dY tile, BN channels x 128 pixels
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NS * A_BYTES;
+  int* offs = reinterpret_cast<int*>(sB + NS * B_BYTES);             // [NS][2*P + 128]
+  const int OFFS_PER = 2 * p.P + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(offs + NS * OFFS_PER) + 15) & ~uintptr_t(15));
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* acc_full = bars + 2 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  // ---- CTA work item
+  int wi = blockIdx.x;
+  const int co_t = wi % p.co_tiles; wi /= p.co_tiles;
+  const int ci_t = wi % p.ci_tiles; wi /= p.ci_tiles;
+  const int grp = wi;                                   // tap group
+  const int split = blockIdx.y, nsplit = gridDim.y;
+  const int ci0 = ci_t * 128, co0 = co_t * p.BN;
+  const int taps_hw = p.kh * p.kw;
+  // taps of this group: tap = tap0 + g, g in [0, G)
+  const int tap0 = grp * p.G;
+  const int gdz = tap0 / taps_hw;                       // depth tap of the group (G <= kh*kw => one dz per group)
+  const int gth0 = (tap0 % taps_hw) / p.kw;             // first kernel row of the group
+  const int gtw0 = (p.G == 1) ? (tap0 % p.kw) : 0;      // single-tap groups stage only that tap's columns
+  const int hd = p.kd >> 1, hh = p.kh >> 1, hw = p.kw >> 1;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { tc::mbar_init(&full[i], WG_PROD); tc::mbar_init(&empty[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // position-tile iteration (identical in every role): tile t -> (n, d, th, tw) or flat index
+  auto tile_valid = [&](long long t, int& n_img, int& d0, int& h0, int& w0, long long& m0) -> bool {
+    if (p.flat) { m0 = t * 128; n_img = d0 = h0 = w0 = 0; return true; }
+    long long r = t;
+    const int tw_ = (int)(r % p.tiles_w); r /= p.tiles_w;
+    const int th_ = (int)(r % p.tiles_h); r /= p.tiles_h;
+    d0 = (int)(r % p.D); n_img = (int)(r / p.D);
+    h0 = th_ * 16; w0 = tw_ * 8; m0 = 0;
+    const int vd = d0 - hd + gdz;
+    return vd >= 0 && vd < p.D;                          // the group's depth slab lies outside: no contribution
+  };
+
+  if (warp < 8) {
+    // =================================================================== producers
+    int st = 0;
+    uint32_t ph = 0;
+    bool produced = false;
+    for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
+      int n_img, d0, h0, w0;
+      long long m0;
+      if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
+      produced = true;
+      tc::mbar_wait(&empty[st], ph ^ 1);
+      int* of = offs + st * OFFS_PER;
+      // pixel offsets of the patch (per source) and of the dY tile
+      for (int i = tid; i < p.nsrc * p.P + 128; i += WG_PROD) {
+        int off = -1;
+        if (i < p.nsrc * p.P) {
+          const int s = i / p.P, q = i - s * p.P;
+          const hdn_src& S = p.src[s];
+          if (p.flat) {
+            if (m0 + q < p.M) off = q * S.t.ldc;
+          } else {
+            const int vh = h0 - hh + gth0 + q / p.PW, vw = w0 - hw + gtw0 + q % p.PW;
+            if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
+              const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
+              off = (sh * S.W + sw) * S.t.ldc;
+            }
+          }
+          of[i] = off;
+        } else {
+          const int r = i - p.nsrc * p.P;
+          if (p.flat) {
+            if (m0 + r < p.M) off = r * p.dy.ldc;
+          } else {
+            const int oh = h0 + (r >> 3), ow = w0 + (r & 7);
+            if (oh < p.H && ow < p.W) off = (oh * p.W + ow) * p.dy.ldc;
+          }
+          of[2 * p.P + r] = off;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float* base[2] = {nullptr, nullptr};
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (s < p.nsrc) {
+          const hdn_src& S = p.src[s];
+          if (p.flat) base[s] = S.t.p + m0 * S.t.ldc + S.t.coff;
+          else {
+            const int vd = d0 - hd + gdz;
+            const int sd = (S.ud == 2) ? (vd >> 1) : vd;
+            base[s] = S.t.p + ((long long)n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+          }
+        }
+      }
+      uint8_t* dA = sA + st * A_BYTES;
+      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0, p.Cin, dA, 8, warp, lane);
+      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0 + 64, p.Cin, dA + 8u * p.Ppad * 16u, 8, warp, lane);
+      // dY tile: plain tensor, no prologue
+      hdn_src dys;
+      dys.t = p.dy; dys.pa = nullptr; dys.pb = nullptr; dys.relu = 0;
+      const float* dbase[2];
+      dbase[0] = p.flat ? (p.dy.p + m0 * p.dy.ldc + p.dy.coff)
+                        : (p.dy.p + ((long long)n_img * p.D + d0) * p.H * p.W * p.dy.ldc + p.dy.coff);
+      dbase[1] = nullptr;
+      uint8_t* dB = sB + st * B_BYTES;
+      for (int cb = 0; cb < p.BN; cb += 64)
+        stage_block(&dys, 1, dbase, of + 2 * p.P, 128, 129, co0 + cb, min(p.Cout, co0 + p.BN), dB + (uint32_t)(cb / 8) * 129u * 16u,
+                    (p.BN - cb + 7) / 8, warp, lane);
+      tc::fence_proxy_async_smem();
+      tc::mbar_arrive(&full[st]);
+      if (++st == NS) { st = 0; ph ^= 1; }
+    }
+
+    // =================================================================== epilogue: TMEM -> dW (vector reductions)
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+    const int q4 = warp & 3;                 // TMEM lane quarter this warp may read
+    const int ci = ci0 + q4 * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const bool vec = (p.Cout % 4 == 0);
+    float v[16];
+    // a CTA whose tap group never met a valid depth slab issued no MMA: its accumulators are undefined
+    for (int g = (warp >> 2); produced && g < p.G; g += 2) {       // warps 0-3 take even taps, warps 4-7 odd
+      const int tap = tap0 + g;
+      for (int cc = 0; cc < p.BN; cc += 16) {
+        tc::tmem_ld16(taddr + (uint32_t)(g * p.BN + cc), v);
+        if (ci < p.Cin) {
+          float* q = p.dw + ((long long)tap * p.Cin + ci) * p.Cout + co0 + cc;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const int col = co0 + cc + i;
+            if (vec) {
+              if (col < p.Cout)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + i), "f"(v[i]), "f"(v[i + 1]),
+                             "f"(v[i + 2]), "f"(v[i + 3])
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col + j < p.Cout) atomicAdd(q + i + j, v[i + j]);
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // =================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 1, 1);
+      const uint32_t a_lbo = (uint32_t)p.PW * 16u, a_sbo = (uint32_t)p.Ppad * 16u;   // K-group / MN-group strides
+      const uint32_t b_lbo = 128u, b_sbo = 129u * 16u;
+      int st = 0;
+      uint32_t ph = 0, acc = 0;
+      for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
+        int n_img, d0, h0, w0;
+        long long m0;
+        if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
+        tc::mbar_wait(&full[st], ph);
+        tc::tc_fence_after();
+        const uint32_t a_stage = tc::smem_u32(sA + st * A_BYTES);
+        const uint32_t b_stage = tc::smem_u32(sB + st * B_BYTES);
+        for (int g = 0; g < p.G; ++g) {
+          const int t2 = (tap0 + g) % taps_hw;
+          const int th = t2 / p.kw - gth0, tw = t2 % p.kw - gtw0;     // relative to the group's patch
+          for (int r = 0; r < 8; ++r) {
+            const uint64_t ad = tc::make_smem_desc(a_stage + (uint32_t)((th + 2 * r) * p.PW + tw) * 16u, a_lbo, a_sbo);
+            const uint64_t bd = tc::make_smem_desc(b_stage + (uint32_t)r * 256u, b_lbo, b_sbo);
+            tc::umma_bf16(tmem_base + (uint32_t)(g * p.BN), ad, bd, idesc, (acc | (uint32_t)(r > 0)));   // overwrite only on the very first K step of each tap
+          }
+        }
+        acc = 1;
+        tc::umma_commit(&empty[st]);
+        if (++st == NS) { st = 0; ph ^= 1; }
+      }
+      tc::umma_commit(acc_full);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+struct WgPlan {
+  int BN, G, groups, ci_tiles, co_tiles, flat, PH, PW, P, Ppad, tiles_h, tiles_w, tmem_cols, row_mode;
+  long long n_pos_tiles;
+  size_t smem;
+  int splits;
+};
+
+bool wg_plan(const hdn_conv* c, WgPlan& best) {
+  const int T = c->kd * c->kh * c->kw, taps_hw = c->kh * c->kw;
+  bool up = false;
+  for (int i = 0; i < c->nsrc; ++i) up = up || c->src[i].ud != 1 || c->src[i].uh != 1 || c->src[i].uw != 1;
+  const int flat = (T == 1 && !up) ? 1 : 0;
+  const int ci_tiles = (c->Cin + 127) / 128;
+  double best_cost = 1e300;
+  bool found = false;
+  const int cand[3] = {taps_hw, c->kw, 1};       // taps per group: one depth slab, one kernel row, a single tap
+  for (int k = 0; k < 3; ++k) {
+    const int G = cand[k];
+    if (k > 0 && G == cand[k - 1]) continue;
+    int bn_max = (512 / G) / 16 * 16;
+    if (bn_max > 256) bn_max = 256;
+    if (bn_max < 16) continue;
+    WgPlan pl;
+    pl.G = G; pl.groups = T / G; pl.ci_tiles = ci_tiles; pl.flat = flat;
+    pl.co_tiles = (c->Cout + bn_max - 1) / bn_max;
+    int bn = (c->Cout + pl.co_tiles - 1) / pl.co_tiles;
+    pl.BN = (bn + 15) / 16 * 16;
+    const int rows = (G == taps_hw) ? c->kh : 1;  // kernel rows covered by a group
+    const int cols = (G == 1) ? 1 : c->kw;
+    pl.row_mode = (G == taps_hw) ? 0 : 1;
+    pl.PH = 16 + rows - 1;
+    pl.PW = 8 + cols - 1;
+    if (G == 1) pl.PW = 8;
+    pl.P = pl.PH * pl.PW;
+    pl.Ppad = pl.P | 1;
+    pl.tiles_h = (c->H + 15) / 16;
+    pl.tiles_w = (c->W + 7) / 8;
+    const long long M = (long long)c->N * c->D * c->H * c->W;
+    pl.n_pos_tiles = flat ? (M + 127) / 128 : (long long)c->N * c->D * pl.tiles_h * pl.tiles_w;
+    int cols_t = 32;
+    while (cols_t < G * pl.BN) cols_t *= 2;
+    pl.tmem_cols = cols_t;
+    const size_t a_bytes = 16ull * pl.Ppad * 16, b_bytes = (size_t)((pl.BN + 7) / 8) * 129 * 16;
+    pl.smem = NS * (a_bytes + b_bytes) + NS * (2ull * pl.P + 128) * 4 + 16 + (2 * NS + 1) * 8 + 16;
+    if (pl.smem > 220 * 1024) continue;
+    const double cost = (double)pl.ci_tiles * pl.co_tiles * pl.groups * ((double)pl.P * 128 * c->nsrc + 128.0 * pl.BN);
+    if (cost < best_cost) { best_cost = cost; best = pl; found = true; }
+  }
+  if (!found) return false;
+  const long long items = (long long)best.ci_tiles * best.co_tiles * best.groups;
+  long long splits = 148 / items;
+  if (splits < 1) splits = 1;
+  if (splits > best.n_pos_tiles) splits = best.n_pos_tiles;
+  best.splits = (int)splits;
+  return true;
+}
+
+}  // namespace
+
+int hdn_wgrad_tc_supported(const hdn_conv* c) {
+  if (c->sd != 1 || c->sh != 1 || c->sw != 1) return 0;
+  const bool k111 = c->kd == 1 && c->kh == 1 && c->kw == 1;
+  const bool k133 = c->kd == 1 && c->kh == 3 && c->kw == 3;
+  const bool k333 = c->kd == 3 && c->kh == 3 && c->kw == 3;
+  if (!(k111 || k133 || k333)) return 0;
+  if (c->pd != c->kd / 2 || c->ph != c->kh / 2 || c->pw != c->kw / 2) return 0;
+  const hdn_src& s0 = c->src[0];
+  if (c->D != s0.D * s0.ud || c->H != s0.H * s0.uh || c->W != s0.W * s0.uw) return 0;
+  for (int i = 0; i < c->nsrc; ++i) {
+    const hdn_src& s = c->src[i];
+    if (s.t.ldc % 4 || s.t.coff % 4 || (reinterpret_cast<uintptr_t>(s.t.p) & 15) != 0) return 0;
+  }
+  if (c->y.ldc % 4 || c->y.coff % 4 || (reinterpret_cast<uintptr_t>(c->y.p) & 15) != 0) return 0;
+  if (c->Cin % 8 || c->Cout % 8) return 0;
+  WgPlan pl;
+  return wg_plan(c, pl) ? 1 : 0;
+}
+
+int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
+  WgPlan pl;
+  HDN_CHECK_ARG(wg_plan(c, pl), "conv_wgrad tc: no plan for this shape");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { hdn_set_error("conv_wgrad tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
+    attr_set = true;
+  }
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = c->N; p.D = c->D; p.H = c->H; p.W = c->W;
+  p.kd = c->kd; p.kh = c->kh; p.kw = c->kw;
+  p.Cin = c->Cin; p.Cout = c->Cout;
+  p.BN = pl.BN; p.G = pl.G; p.groups = pl.groups; p.ci_tiles = pl.ci_tiles; p.co_tiles = pl.co_tiles;
+  p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad; p.row0_mode = pl.row_mode;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_pos_tiles = pl.n_pos_tiles;
+  p.M = (long long)c->N * c->D * c->H * c->W;
+  p.nsrc = c->nsrc; p.src[0] = c->src[0]; p.src[1] = c->src[1];
+  p.dy = c->y; p.dw = dw; p.tmem_cols = pl.tmem_cols;
+  dim3 grid((unsigned)(pl.ci_tiles * pl.co_tiles * pl.groups), (unsigned)pl.splits);
+  conv_wgrad_tc_kernel<<<grid, WG_THREADS, pl.smem, st>>>(p);
+  HDN_CHECK_LAUNCH("conv_wgrad_tc");
+  return HDN_OK;
+}

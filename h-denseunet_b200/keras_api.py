@@ -66,6 +66,7 @@ class Model(object):
         self.dp = None
         self.stop_training = False
         self._staging = {}
+        self._staging_ev = {}
         # register every parameter (host values, Keras default initialisers) without touching a device
         self._build(engine.Net(self.params, "meta", True, "fp32", backend=object(), dropout=False))
 
@@ -136,12 +137,19 @@ class Model(object):
             st = (torch.empty(x.shape, dtype=torch.float32, pin_memory=pin),
                   torch.empty(x.shape, dtype=torch.float32, device=dst.device) if three_d else None)
             self._staging[key] = st
+        ev = self._staging_ev.get(key)
+        if ev is not None:
+            ev.synchronize()          # the previous async copy out of this pinned buffer must have finished
         st[0].copy_(torch.from_numpy(x))
         if three_d:    # (N,H,W,S,C) -> (N,S,H,W,C)
             st[1].copy_(st[0], non_blocking=True)
             dst.copy_(st[1].permute(0, 3, 1, 2, 4))
         else:
             dst.view(x.shape).copy_(st[0], non_blocking=True)
+        if dst.device.type == "cuda":
+            if ev is None:
+                ev = self._staging_ev[key] = torch.cuda.Event()
+            ev.record()
 
     def _labels(self, net, y):
         y = np.asarray(y, dtype=np.float32)

@@ -126,7 +126,7 @@ def load():
         "hdn_col_stats": [Tensor, i64, i32, vp, vp, vp],
         "hdn_wce_accum": [vp, vp, i64, i32, i64, i32, i32, vp, vp],
         "hdn_wce_grad": [vp, vp, vp, i64, i32, i64, i32, i32, vp, f32, vp],
-        "hdn_triplets": [vp, vp, i32, i32, i64, vp],
+        "hdn_triplets": [vp, vp, i32, i32, i64, i32, vp],
         "hdn_cat4": [vp, vp, vp, i64, f32, vp],
         "hdn_cat4_bwd": [vp, vp, i64, f32, i32, vp],
         "hdn_sgd_nesterov": [vp, vp, vp, i64, f32, f32, f32, vp],

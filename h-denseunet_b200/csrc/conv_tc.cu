@@ -43,6 +43,11 @@ struct TcParams {
   hdn_src src[2];             // A operand sources
   const __nv_bfloat16* wpack;
   int mode;                   // 0 fprop, 1 dgrad
+  int pd_lo, ph_lo, pw_lo;    // patch origin = tile origin - p*_lo (padding in front of tap 0)
+  int s2d;                    // 1: A operand is the space-to-depth view of a stride-2 convolution's input:
+                              //    s2d pixel (d,h,w) holds channels (rd,rh,rw,c) = x[2d+rd][2h+rh][2w+rw][c], ldc == 4
+  int s2d_quads;              //    4-channel quads per s2d pixel: 8 (3-D) or 4 (2-D)
+  int scatter;                // 1: dgrad epilogue writes the (rd,rh,rw,c) columns back to x's positions
   // fprop epilogue
   const float* bias;
   hdn_tensor y;
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     d0 = t % p.D; n_img = t / p.D;
     h0 = th_ * 16; w0 = tw_ * 8;
   }
-  const int hh = p.kh >> 1, hw = p.kw >> 1, hd = p.kd >> 1;
+  const int hh = p.ph_lo, hw = p.pw_lo, hd = p.pd_lo;
 
   // ---- one-time setup
   for (int i = tid; i < p.nsrc * p.P; i += TC_THREADS) {
@@ -107,8 +112,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     } else {
       const int vh = h0 - hh + q / p.PW, vw = w0 - hw + q % p.PW;
       if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
-        const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
-        off = (sh * S.W + sw) * S.t.ldc;
+        if (p.s2d) off = (2 * vh * S.W + 2 * vw) * S.t.ldc;
+        else {
+          const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
+          off = (sh * S.W + sw) * S.t.ldc;
+        }
       }
     }
     pix[i] = off;
@@ -139,7 +147,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
     for (int kb = 0; kb < p.KB; ++kb) {
       const int c0 = kb * 64;
       const int cA = c0 + l8 * 4, cB = c0 + 32 + l8 * 4;       // this lane's two channel quads
-      const bool okA = cA < p.K, okB = cB < p.K;               // K % 8 == 0, so a quad is all-in or all-out
+      bool okA = cA < p.K, okB = cB < p.K;                     // K % 8 == 0, so a quad is all-in or all-out
+      int s2d_rd = 0, s2d_add = 0;
+      if (p.s2d) {                                             // quad l8 = (rd, rh, rw): 8 floats (rw, c) are contiguous in x
+        okA = l8 < p.s2d_quads; okB = false;
+        s2d_rd = (p.s2d_quads == 8) ? (l8 >> 2) : 0;
+        s2d_add = ((l8 >> 1) & 1) * p.src[0].W * p.src[0].t.ldc + (l8 & 1) * 4 - cA;   // "- cA": the generic code adds cA
+      }
       float4 a0[2], b0[2], a1[2], b1[2];
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
@@ -162,6 +176,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             const hdn_src& S = p.src[s];
             if (p.flat) {
               base[s] = S.t.p + m0 * S.t.ldc + S.t.coff;
+            } else if (p.s2d) {
+              base[s] = S.t.p + ((long long)n_img * S.D + (p.s2d_quads == 8 ? 2 * vd + s2d_rd : vd)) * S.H * S.W * S.t.ldc + S.t.coff + s2d_add;
             } else {
               const int sd = (S.ud == 2) ? (vd >> 1) : vd;
               base[s] = S.t.p + ((long long)n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
@@ -289,6 +305,27 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
             atomicAdd(p.stat_sum + col, (double)sstat[c]);
             atomicAdd(p.stat_sq + col, (double)sstat[p.BN + c]);
           }
+        }
+      }
+    } else if (p.scatter) {
+      // dgrad of a stride-2 stem in space-to-depth form: column (rd,rh,rw,c) of s2d pixel (d0,oh,ow) is the
+      // gradient of x[2*d0+rd][2*oh+rh][2*ow+rw][c]; the input has no prologue (hybridnet.py:122-123,208-209)
+      const hdn_dgrad_epi& E = p.epi[0];
+      const hdn_src& S = p.esrc[0];
+      for (int cc = 0; cc < p.BN; cc += 16) {
+        tc::tmem_ld16(taddr + cc, v);
+        if (!rvalid) continue;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const int qd = (n_tile * p.BN + cc + i) >> 2;
+          if (qd >= p.s2d_quads) continue;
+          const int rd = (p.s2d_quads == 8) ? (qd >> 2) : 0, rh = (qd >> 1) & 1, rw = qd & 1;
+          const int sd = (p.s2d_quads == 8) ? (2 * d0 + rd) : d0;
+          const long long ms = (((long long)n_img * S.D + sd) * S.H + 2 * oh + rh) * S.W + 2 * ow + rw;
+          float* q = const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff;
+          float4 g = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+          *reinterpret_cast<float4*>(q) = g;
         }
       }
     } else {
@@ -495,6 +532,46 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
+// Stride-2 stems in space-to-depth form (7-tap kernel, pad 3, stride 2 == 4-tap kernel over the s2d input):
+// s2d tap tq (0..3) and sub-position r (0/1) read original tap t = 2*tq + r - 1 (t = -1 does not exist -> 0).
+//   role 0 (fprop): B[n = co][k = (rd,rh,rw,c)] = w[t(tq,r)][c][co]
+//   role 1 (dgrad): B[n = (rd,rh,rw,c)][k = co] = w[t(3 - tq', r)][c][co]   (taps flipped)
+__global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                                               int Cin, int Cout, int three_d, int BN, int KB, int role,
+                                                               long long total16) {
+  const int TD = three_d ? 4 : 1, T = TD * 16;
+  const int quads = three_d ? 8 : 4;
+  const int K = role == 0 ? quads * 4 : Cout, NC = role == 0 ? Cout : quads * 4;
+  const int k7d = three_d ? 7 : 1;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total16; idx += (long long)gridDim.x * 256) {
+    long long t = idx;
+    const int n = (int)(t % BN); t /= BN;
+    const int j = (int)(t % 8); t /= 8;
+    int tap = (int)(t % T); t /= T;
+    const int kb = (int)(t % KB); t /= KB;
+    const int nt = (int)t;
+    if (role == 1) tap = T - 1 - tap;
+    const int tqw = tap & 3, tqh = (tap >> 2) & 3, tqd = tap >> 4;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kb * 64 + j * 8 + e, col = nt * BN + n;
+      v[e] = 0.f;
+      if (k < K && col < NC) {
+        const int sc = role == 0 ? k : col, co = role == 0 ? col : k;    // s2d channel (rd,rh,rw,c), output channel
+        const int c = sc & 3, rw = (sc >> 2) & 1, rh = (sc >> 3) & 1, rd = (sc >> 4) & 1;
+        const int tw = 2 * tqw + rw - 1, th = 2 * tqh + rh - 1, td = three_d ? (2 * tqd + rd - 1) : 0;
+        if (c < Cin && tw >= 0 && th >= 0 && td >= 0 && tw < 7 && th < 7 && td < k7d)
+          v[e] = __ldg(w + ((((long long)td * 7 + th) * 7 + tw) * Cin + c) * Cout + co);
+      }
+    }
+    uint4 o;
+    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
+    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[idx] = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) zero_window_kernel(hdn_tensor t, long long M, int C) {
   const long long total = M * C;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -530,19 +607,56 @@ bool tc_y_aligned(const hdn_conv* c) {
   return c->y.ldc % 4 == 0 && c->y.coff % 4 == 0 && (reinterpret_cast<uintptr_t>(c->y.p) & 15) == 0;
 }
 
-TcPlan tc_plan(const hdn_conv* c, int K, int NC) {
-  TcPlan pl;
-  pl.n_tiles = (NC + 255) / 256;
-  int bn = (NC + pl.n_tiles - 1) / pl.n_tiles;
-  pl.BN = (bn + 15) / 16 * 16;
-  pl.KB = (K + 63) / 64;
-  const hdn_src& s0 = c->src[0];
+// Stride-2 stems (hybridnet.py:122-123 3dconv1 7x7x7/2, :208-209 conv1 7x7/2, after ZeroPadding 3) run on the
+// tensor cores in space-to-depth form.  Returns 3 / 2 for the 3-D / 2-D stem, 0 otherwise.
+int tc_stem(const hdn_conv* c) {
+  const bool k3 = c->kd == 7 && c->kh == 7 && c->kw == 7 && c->sd == 2 && c->sh == 2 && c->sw == 2 && c->pd == 3 &&
+                  c->ph == 3 && c->pw == 3;
+  const bool k2 = c->kd == 1 && c->kh == 7 && c->kw == 7 && c->sd == 1 && c->sh == 2 && c->sw == 2 && c->pd == 0 &&
+                  c->ph == 3 && c->pw == 3;
+  if (!k3 && !k2) return 0;
+  const hdn_src& s = c->src[0];
+  if (c->nsrc != 1 || s.ud != 1 || s.uh != 1 || s.uw != 1 || s.pa || s.pb || s.relu) return 0;
+  if (s.t.ldc != 4 || s.t.coff != 0 || c->Cin > 4 || (reinterpret_cast<uintptr_t>(s.t.p) & 15) != 0) return 0;
+  if ((s.H & 1) || (s.W & 1) || c->H != s.H / 2 || c->W != s.W / 2) return 0;
+  if (k3 && ((s.D & 1) || c->D != s.D / 2)) return 0;
+  if (k2 && c->D != s.D) return 0;
+  if (c->Cout % 8) return 0;
+  return k3 ? 3 : 2;
+}
+
+struct TcGeom { int kd, kh, kw, pd_lo, ph_lo, pw_lo, K, NC, flat, s2d, quads, scatter; };
+
+TcGeom tc_geom(const hdn_conv* c, int mode) {
+  TcGeom g;
+  memset(&g, 0, sizeof(g));
+  const int stem = tc_stem(c);
+  if (stem) {
+    g.kd = stem == 3 ? 4 : 1; g.kh = 4; g.kw = 4;
+    g.quads = stem == 3 ? 8 : 4;
+    if (mode == 0) { g.pd_lo = stem == 3 ? 2 : 0; g.ph_lo = 2; g.pw_lo = 2; g.K = g.quads * 4; g.NC = c->Cout; g.s2d = 1; }
+    else { g.pd_lo = stem == 3 ? 1 : 0; g.ph_lo = 1; g.pw_lo = 1; g.K = c->Cout; g.NC = g.quads * 4; g.scatter = 1; }
+    return g;
+  }
+  g.kd = c->kd; g.kh = c->kh; g.kw = c->kw;
+  g.pd_lo = c->kd / 2; g.ph_lo = c->kh / 2; g.pw_lo = c->kw / 2;
+  g.K = mode == 0 ? c->Cin : c->Cout;
+  g.NC = mode == 0 ? c->Cout : c->Cin;
   bool up = false;
   for (int i = 0; i < c->nsrc; ++i) up = up || c->src[i].ud != 1 || c->src[i].uh != 1 || c->src[i].uw != 1;
-  pl.flat = (c->kd == 1 && c->kh == 1 && c->kw == 1 && !up) ? 1 : 0;
-  (void)s0;
-  pl.PH = 16 + c->kh - 1;
-  pl.PW = 8 + c->kw - 1;
+  g.flat = (c->kd == 1 && c->kh == 1 && c->kw == 1 && !up) ? 1 : 0;
+  return g;
+}
+
+TcPlan tc_plan(const hdn_conv* c, const TcGeom& g) {
+  TcPlan pl;
+  pl.n_tiles = (g.NC + 255) / 256;
+  int bn = (g.NC + pl.n_tiles - 1) / pl.n_tiles;
+  pl.BN = (bn + 15) / 16 * 16;
+  pl.KB = (g.K + 63) / 64;
+  pl.flat = g.flat;
+  pl.PH = 16 + g.kh - 1;
+  pl.PW = 8 + g.kw - 1;
   pl.P = pl.PH * pl.PW;
   pl.Ppad = pl.P | 1;
   pl.tiles_h = (c->H + 15) / 16;
@@ -553,14 +667,14 @@ TcPlan tc_plan(const hdn_conv* c, int K, int NC) {
   int cols = 32;
   while (cols < pl.BN) cols *= 2;
   pl.tmem_cols = cols;
-  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (c->kd * c->kh * c->kw) * pl.BN * 64;
+  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * 64;
   pl.smem = NSA * a_bytes + pl.nsb * b_bytes + 2ull * pl.P * 4 + 4ull * pl.BN * 4 + 16 + (2 * NSA + 2 * NSB_MAX + 1) * 8 + 16;
   return pl;
 }
 
 int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_t st) {
-  const int K = mode == 0 ? c->Cin : c->Cout, NC = mode == 0 ? c->Cout : c->Cin;
-  const TcPlan pl = tc_plan(c, K, NC);
+  const TcGeom g = tc_geom(c, mode);
+  const TcPlan pl = tc_plan(c, g);
   HDN_CHECK_ARG(c->ws != nullptr && c->ws_bytes >= pl.ws_elems * 2, "conv tc: workspace too small (%lld < %lld bytes)",
                 (long long)c->ws_bytes, (long long)pl.ws_elems * 2);
   static bool attr_set = false;
@@ -572,15 +686,20 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(c->ws);
   {
     long long total = pl.ws_elems / 8;
-    unsigned g = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-    pack_weights_kernel<<<g, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.n_tiles, mode, total);
+    unsigned gr = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    if (g.s2d || g.scatter)
+      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, mode, total);
+    else
+      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.n_tiles, mode, total);
     HDN_CHECK_LAUNCH("pack_weights");
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.N = c->N; p.D = c->D; p.H = c->H; p.W = c->W;
-  p.kd = c->kd; p.kh = c->kh; p.kw = c->kw;
-  p.K = K; p.NC = NC;
+  p.kd = g.kd; p.kh = g.kh; p.kw = g.kw;
+  p.pd_lo = g.pd_lo; p.ph_lo = g.ph_lo; p.pw_lo = g.pw_lo;
+  p.s2d = g.s2d; p.s2d_quads = g.quads; p.scatter = g.scatter;
+  p.K = g.K; p.NC = g.NC;
   p.BN = pl.BN; p.KB = pl.KB; p.nsb = pl.nsb; p.tmem_cols = pl.tmem_cols;
   p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
@@ -607,12 +726,15 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
       if (epi[i].mode == 2) continue;
       const hdn_src& s = c->src[i];
       HDN_CHECK_ARG(epi[i].mode != 0 || (epi[i].dx.ldc % 4 == 0 && epi[i].dx.coff % 4 == 0), "conv_dgrad tc: dx window not 16-byte aligned");
+      if (g.scatter)
+        HDN_CHECK_ARG(epi[i].mode == 0 && epi[i].s1 == nullptr && epi[i].dx.ldc == 4 && epi[i].dx.coff == 0,
+                      "conv_dgrad tc: the stem input gradient must be a plain 4-channel tensor");
       if (s.ud == 2 && !epi[i].accumulate) {
         // depth sub-positions live in different CTAs and are combined with atomics: start from zero
         const long long Ms = (long long)c->N * s.D * s.H * s.W;
         if (epi[i].mode == 0) {
-          unsigned g = (unsigned)((Ms * c->Cin + 255) / 256 > 148 * 16 ? 148 * 16 : (Ms * c->Cin + 255) / 256);
-          zero_window_kernel<<<g, 256, 0, st>>>(epi[i].dx, Ms, c->Cin);
+          unsigned gr = (unsigned)((Ms * c->Cin + 255) / 256 > 148 * 16 ? 148 * 16 : (Ms * c->Cin + 255) / 256);
+          zero_window_kernel<<<gr, 256, 0, st>>>(epi[i].dx, Ms, c->Cin);
           HDN_CHECK_LAUNCH("zero_window");
         } else {
           cudaError_t e = cudaMemsetAsync(epi[i].du, 0, (size_t)Ms * c->Cin * sizeof(float), st);
@@ -632,8 +754,14 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
 }  // namespace
 
 int hdn_wgrad_tc_supported(const hdn_conv* c);
+int hdn_tc_stem(const hdn_conv* c) { return tc_stem(c); }
 
 int hdn_tc_supported(const hdn_conv* c, int pass) {
+  if (tc_stem(c)) {
+    if (pass == 0) return 1;
+    if (pass == 1) return tc_y_aligned(c) ? 1 : 0;
+    return hdn_wgrad_tc_supported(c);
+  }
   if (!tc_shape_ok(c)) return 0;
   if (pass == 0) return (c->Cin % 8 == 0) ? 1 : 0;
   if (pass == 1) return (c->Cout % 8 == 0 && c->Cin % 8 == 0 && tc_y_aligned(c)) ? 1 : 0;   // dY is the A operand
@@ -642,8 +770,7 @@ int hdn_tc_supported(const hdn_conv* c, int pass) {
 
 long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
   if (!hdn_tc_supported(c, pass) || pass == 2) return 0;
-  const int K = pass == 0 ? c->Cin : c->Cout, NC = pass == 0 ? c->Cout : c->Cin;
-  return tc_plan(c, K, NC).ws_elems * 2;
+  return tc_plan(c, tc_geom(c, pass)).ws_elems * 2;
 }
 
 int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st) { return tc_launch(c, nullptr, 0, st); }

@@ -16,6 +16,8 @@
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
+int hdn_tc_stem(const hdn_conv* c);   // conv_tc.cu
+
 namespace {
 
 constexpr int WG_THREADS = 288;
@@ -32,6 +34,9 @@ struct WgParams {
   int flat;
   int PH, PW, P, Ppad;         // patch of ONE tap group (rows PH, cols PW)
   int row0_mode;               // 0: group covers all kh rows; 1: group g covers kernel row (g % kh) only
+  int pd_lo, ph_lo, pw_lo;     // padding in front of tap 0
+  int s2d, s2d_quads;          // stride-2 stem in space-to-depth form (see conv_tc.cu); Cin here = 4 * quads
+  int cin_real;                //   real input channels of the stem (<= 4)
   int tiles_w, tiles_h;
   long long n_pos_tiles;       // position tiles per slice set
   long long M;
@@ -54,12 +59,13 @@ __device__ __forceinline__ float4 pro4(float4 x, float4 a, float4 b, int relu) {
 // ppad*16 bytes).  offs[s*npx + q] is the element offset of pixel q in source s (or -1 => zeros).
 __device__ __forceinline__ void stage_block(const hdn_src* src, int nsrc, const float* const* base, const int* offs,
                                             int npx, int ppad, int cbase, int climit, uint8_t* dst, int nchunks,
-                                            int pwarp, int lane) {
+                                            int pwarp, int lane, int s2d_quads = 0) {
   const int l8 = lane & 7, pg = lane >> 3;
   const bool even = (l8 & 1) == 0;
   const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
   const int cA = cbase + l8 * 4, cB = cbase + 32 + l8 * 4;
-  const bool okA = cA < climit, okB = cB < climit;
+  bool okA = cA < climit, okB = cB < climit;
+  if (s2d_quads) { okA = cbase == 0 && l8 < s2d_quads; okB = false; }   // base[] already points at this lane's 8 floats - cA
   float4 a0[2], b0[2], a1[2], b1[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   const int gdz = tap0 / taps_hw;                       // depth tap of the group (G <= kh*kw => one dz per group)
   const int gth0 = (tap0 % taps_hw) / p.kw;             // first kernel row of the group
   const int gtw0 = (p.G == 1) ? (tap0 % p.kw) : 0;      // single-tap groups stage only that tap's columns
-  const int hd = p.kd >> 1, hh = p.kh >> 1, hw = p.kw >> 1;
+  const int hd = p.pd_lo, hh = p.ph_lo, hw = p.pw_lo;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { tc::mbar_init(&full[i], WG_PROD); tc::mbar_init(&empty[i], 1); }
@@ -192,8 +198,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           } else {
             const int vh = h0 - hh + gth0 + q / p.PW, vw = w0 - hw + gtw0 + q % p.PW;
             if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
-              const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
-              off = (sh * S.W + sw) * S.t.ldc;
+              if (p.s2d) off = (2 * vh * S.W + 2 * vw) * S.t.ldc;
+              else {
+                const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
+                off = (sh * S.W + sw) * S.t.ldc;
+              }
             }
           }
           of[i] = off;
@@ -217,14 +226,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           if (p.flat) base[s] = S.t.p + m0 * S.t.ldc + S.t.coff;
           else {
             const int vd = d0 - hd + gdz;
-            const int sd = (S.ud == 2) ? (vd >> 1) : vd;
-            base[s] = S.t.p + ((long long)n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+            if (p.s2d) {
+              const int l8 = lane & 7;
+              const int rd = (p.s2d_quads == 8) ? (l8 >> 2) : 0;
+              base[s] = S.t.p + ((long long)n_img * S.D + (p.s2d_quads == 8 ? 2 * vd + rd : vd)) * S.H * S.W * S.t.ldc + S.t.coff +
+                        ((l8 >> 1) & 1) * S.W * S.t.ldc + (l8 & 1) * 4 - (ci0 + l8 * 4);
+            } else {
+              const int sd = (S.ud == 2) ? (vd >> 1) : vd;
+              base[s] = S.t.p + ((long long)n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+            }
           }
         }
       }
       uint8_t* dA = sA + st * A_BYTES;
-      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0, p.Cin, dA, 8, warp, lane);
-      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0 + 64, p.Cin, dA + 8u * p.Ppad * 16u, 8, warp, lane);
+      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0, p.Cin, dA, 8, warp, lane, p.s2d ? p.s2d_quads : 0);
+      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0 + 64, p.Cin, dA + 8u * p.Ppad * 16u, 8, warp, lane, p.s2d ? p.s2d_quads : 0);
       // dY tile: plain tensor, no prologue
       hdn_src dys;
       dys.t = p.dy; dys.pa = nullptr; dys.pb = nullptr; dys.relu = 0;
@@ -254,8 +270,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       const int tap = tap0 + g;
       for (int cc = 0; cc < p.BN; cc += 16) {
         tc::tmem_ld16(taddr + (uint32_t)(g * p.BN + cc), v);
-        if (ci < p.Cin) {
-          float* q = p.dw + ((long long)tap * p.Cin + ci) * p.Cout + co0 + cc;
+        long long wrow = (long long)tap * p.Cin + ci;        // row of dW [tap][ci]
+        bool rok = ci < p.Cin;
+        if (p.s2d) {
+          // s2d tap (tqd,tqh,tqw) x s2d channel (rd,rh,rw,c)  ->  original tap t = 2*tq + r - 1 (per axis), channel c
+          const int c = ci & 3, rw = (ci >> 2) & 1, rh = (ci >> 3) & 1, rd = (ci >> 4) & 1;
+          const int tqw = tap & 3, tqh = (tap >> 2) & 3, tqd = tap >> 4;
+          const int tw = 2 * tqw + rw - 1, th = 2 * tqh + rh - 1, td = (p.s2d_quads == 8) ? (2 * tqd + rd - 1) : 0;
+          const int k7d = (p.s2d_quads == 8) ? 7 : 1;
+          rok = rok && c < p.cin_real && tw >= 0 && th >= 0 && td >= 0 && tw < 7 && th < 7 && td < k7d;
+          wrow = (((long long)td * 7 + th) * 7 + tw) * p.cin_real + c;
+        }
+        if (rok) {
+          float* q = p.dw + wrow * p.Cout + co0 + cc;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             const int col = co0 + cc + i;
@@ -321,15 +348,32 @@ struct WgPlan {
   int splits;
 };
 
-bool wg_plan(const hdn_conv* c, WgPlan& best) {
-  const int T = c->kd * c->kh * c->kw, taps_hw = c->kh * c->kw;
+struct WgGeom { int kd, kh, kw, pd_lo, ph_lo, pw_lo, Cin, s2d, quads; };
+
+WgGeom wg_geom(const hdn_conv* c) {
+  WgGeom g;
+  const int stem = hdn_tc_stem(c);
+  if (stem) {
+    g.kd = stem == 3 ? 4 : 1; g.kh = 4; g.kw = 4;
+    g.pd_lo = stem == 3 ? 2 : 0; g.ph_lo = 2; g.pw_lo = 2;
+    g.quads = stem == 3 ? 8 : 4; g.Cin = 4 * g.quads; g.s2d = 1;
+  } else {
+    g.kd = c->kd; g.kh = c->kh; g.kw = c->kw;
+    g.pd_lo = c->kd / 2; g.ph_lo = c->kh / 2; g.pw_lo = c->kw / 2;
+    g.Cin = c->Cin; g.s2d = 0; g.quads = 0;
+  }
+  return g;
+}
+
+bool wg_plan(const hdn_conv* c, const WgGeom& gm, WgPlan& best) {
+  const int T = gm.kd * gm.kh * gm.kw, taps_hw = gm.kh * gm.kw;
   bool up = false;
   for (int i = 0; i < c->nsrc; ++i) up = up || c->src[i].ud != 1 || c->src[i].uh != 1 || c->src[i].uw != 1;
   const int flat = (T == 1 && !up) ? 1 : 0;
-  const int ci_tiles = (c->Cin + 127) / 128;
+  const int ci_tiles = (gm.Cin + 127) / 128;
   double best_cost = 1e300;
   bool found = false;
-  const int cand[3] = {taps_hw, c->kw, 1};       // taps per group: one depth slab, one kernel row, a single tap
+  const int cand[3] = {taps_hw, gm.kw, 1};       // taps per group: one depth slab, one kernel row, a single tap
   for (int k = 0; k < 3; ++k) {
     const int G = cand[k];
     if (k > 0 && G == cand[k - 1]) continue;
@@ -341,8 +385,8 @@ bool wg_plan(const hdn_conv* c, WgPlan& best) {
     pl.co_tiles = (c->Cout + bn_max - 1) / bn_max;
     int bn = (c->Cout + pl.co_tiles - 1) / pl.co_tiles;
     pl.BN = (bn + 15) / 16 * 16;
-    const int rows = (G == taps_hw) ? c->kh : 1;  // kernel rows covered by a group
-    const int cols = (G == 1) ? 1 : c->kw;
+    const int rows = (G == taps_hw) ? gm.kh : 1;  // kernel rows covered by a group
+    const int cols = (G == 1) ? 1 : gm.kw;
     pl.row_mode = (G == taps_hw) ? 0 : 1;
     pl.PH = 16 + rows - 1;
     pl.PW = 8 + cols - 1;
@@ -374,6 +418,11 @@ bool wg_plan(const hdn_conv* c, WgPlan& best) {
 }  // namespace
 
 int hdn_wgrad_tc_supported(const hdn_conv* c) {
+  if (hdn_tc_stem(c)) {
+    if (c->y.ldc % 4 || c->y.coff % 4 || (reinterpret_cast<uintptr_t>(c->y.p) & 15) != 0) return 0;
+    WgPlan pl;
+    return wg_plan(c, wg_geom(c), pl) ? 1 : 0;
+  }
   if (c->sd != 1 || c->sh != 1 || c->sw != 1) return 0;
   const bool k111 = c->kd == 1 && c->kh == 1 && c->kw == 1;
   const bool k133 = c->kd == 1 && c->kh == 3 && c->kw == 3;
@@ -389,12 +438,13 @@ int hdn_wgrad_tc_supported(const hdn_conv* c) {
   if (c->y.ldc % 4 || c->y.coff % 4 || (reinterpret_cast<uintptr_t>(c->y.p) & 15) != 0) return 0;
   if (c->Cin % 8 || c->Cout % 8) return 0;
   WgPlan pl;
-  return wg_plan(c, pl) ? 1 : 0;
+  return wg_plan(c, wg_geom(c), pl) ? 1 : 0;
 }
 
 int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   WgPlan pl;
-  HDN_CHECK_ARG(wg_plan(c, pl), "conv_wgrad tc: no plan for this shape");
+  const WgGeom gm = wg_geom(c);
+  HDN_CHECK_ARG(wg_plan(c, gm, pl), "conv_wgrad tc: no plan for this shape");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -404,8 +454,10 @@ int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.N = c->N; p.D = c->D; p.H = c->H; p.W = c->W;
-  p.kd = c->kd; p.kh = c->kh; p.kw = c->kw;
-  p.Cin = c->Cin; p.Cout = c->Cout;
+  p.kd = gm.kd; p.kh = gm.kh; p.kw = gm.kw;
+  p.pd_lo = gm.pd_lo; p.ph_lo = gm.ph_lo; p.pw_lo = gm.pw_lo;
+  p.s2d = gm.s2d; p.s2d_quads = gm.quads; p.cin_real = c->Cin;
+  p.Cin = gm.Cin; p.Cout = c->Cout;
   p.BN = pl.BN; p.G = pl.G; p.groups = pl.groups; p.ci_tiles = pl.ci_tiles; p.co_tiles = pl.co_tiles;
   p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad; p.row0_mode = pl.row_mode;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_pos_tiles = pl.n_pos_tiles;

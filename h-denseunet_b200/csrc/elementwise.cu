@@ -274,16 +274,18 @@ __global__ void __launch_bounds__(ET) wce_grad_kernel(const float* __restrict__ 
 
 // --------------------------------------------------------------------------- hybrid glue
 __global__ void __launch_bounds__(ET) triplets_kernel(const float* __restrict__ vol, float* __restrict__ out, int B, int S,
-                                                       int64_t HW) {
+                                                       int64_t HW, int ldc) {
   const int64_t total = (int64_t)B * S * HW;
   for (int64_t i = blockIdx.x * (int64_t)ET + threadIdx.x; i < total; i += (int64_t)gridDim.x * ET) {
     int64_t hw = i % HW;
     int s = (int)((i / HW) % S), b = (int)(i / (HW * S));
     const float* base = vol + (int64_t)b * S * HW + hw;
     int sm = s > 0 ? s - 1 : 0, sp = s < S - 1 ? s + 1 : S - 1;
-    out[3 * i] = base[(int64_t)sm * HW];
-    out[3 * i + 1] = base[(int64_t)s * HW];
-    out[3 * i + 2] = base[(int64_t)sp * HW];
+    float* o = out + i * ldc;
+    o[0] = base[(int64_t)sm * HW];
+    o[1] = base[(int64_t)s * HW];
+    o[2] = base[(int64_t)sp * HW];
+    for (int c = 3; c < ldc; ++c) o[c] = 0.f;      // padding channels (16-byte pixels for the tensor-core stem)
   }
 }
 __global__ void __launch_bounds__(ET) cat4_kernel(const float* __restrict__ vol, const float* __restrict__ lg,
@@ -437,9 +439,9 @@ extern "C" int hdn_wce_grad(const float* logits, const float* labels, float* dlo
   HDN_CHECK_LAUNCH("wce_grad");
   return HDN_OK;
 }
-extern "C" int hdn_triplets(const float* vol, float* out, int B, int S, int64_t HW, void* stream) {
-  HDN_CHECK_ARG(vol && out && B > 0 && S > 0 && HW > 0, "triplets: bad arguments");
-  triplets_kernel<<<grid_for((int64_t)B * S * HW, 2), ET, 0, ST>>>(vol, out, B, S, HW);
+extern "C" int hdn_triplets(const float* vol, float* out, int B, int S, int64_t HW, int ldc, void* stream) {
+  HDN_CHECK_ARG(vol && out && B > 0 && S > 0 && HW > 0 && ldc >= 3, "triplets: bad arguments");
+  triplets_kernel<<<grid_for((int64_t)B * S * HW, 2), ET, 0, ST>>>(vol, out, B, S, HW, ldc);
   HDN_CHECK_LAUNCH("triplets");
   return HDN_OK;
 }

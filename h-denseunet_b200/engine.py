@@ -303,7 +303,8 @@ class CudaBackend(object):
                                          acc.data_ptr(), gscale, self.stream), "hdn_wce_grad")
 
     def triplets(self, vol, out, B, S, HW):
-        _lib.check(self._run("triplets", 0.0, 1, self.lib.hdn_triplets, vol.data_ptr(), out.data_ptr(), B, S, HW, self.stream), "hdn_triplets")
+        _lib.check(self._run("triplets", 0.0, 1, self.lib.hdn_triplets, vol.data_ptr(), out.data_ptr(), B, S, HW,
+                             out.shape[-1], self.stream), "hdn_triplets")
 
     def cat4(self, vol, logits, out, M, k):
         _lib.check(self._run("cat4", 0.0, 1, self.lib.hdn_cat4, vol.data_ptr(), logits.data_ptr(), out.data_ptr(), M, k, self.stream), "hdn_cat4")
@@ -768,6 +769,7 @@ class Net(object):
 
     def input(self, name, N, D, H, W, C_):
         b = self.buffer(name, N, D, H, W, C_)
+        b.data.zero_()              # padding channels of an input are never written afterwards
         self.inputs[name] = b
         return b.view()
 

@@ -144,6 +144,9 @@ class Model(object):
         if three_d:    # (N,H,W,S,C) -> (N,S,H,W,C)
             st[1].copy_(st[0], non_blocking=True)
             dst.copy_(st[1].permute(0, 3, 1, 2, 4))
+        elif dst.shape[-1] != x.shape[-1] and dst.dim() == 5 and x.ndim == 4:
+            # 2-D input (N,H,W,3) into the 4-channel padded buffer (N,1,H,W,4); channel 3 stays zero
+            dst[:, 0, :, :, :x.shape[-1]].copy_(st[0], non_blocking=True)
         else:
             dst.view(x.shape).copy_(st[0], non_blocking=True)
         if dst.device.type == "cuda":

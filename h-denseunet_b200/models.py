@@ -155,8 +155,9 @@ def hybrid_net(net, B, S, H, W, mode):
     """hybridnet.py:379-423 / denseunet3d.py:393-439.  Input 'volumetric_data' (B,S,H,W,1).
     The 2-D network's (B*S,1,H,W,C) outputs are re-read in place as (B,S,H,W,C) volumes."""
     vol = net.input("volumetric_data", B, S, H, W, 1)
-    in2d = net.buffer("input2d", B * S, 1, H, W, 3).view()
-    net.triplets(vol, in2d)
+    in2d_buf = net.buffer("input2d", B * S, 1, H, W, 4)      # 3 slices + a zero channel: 16-byte pixels
+    net.triplets(vol, in2d_buf.view())
+    in2d = in2d_buf.view(0, 3)
     feat2d, logits2d = dense_unet_2d(net, in2d, mode)
     in3d = net.buffer("input3d", B, S, H, W, 4).view()
     net.cat4(vol, logits2d.as_nd(B, S), in3d)
@@ -171,7 +172,7 @@ def hybrid_net(net, B, S, H, W, mode):
 
 
 def unet2d_net(net, N, H, W, mode, skip=False):
-    x = net.input("data", N, 1, H, W, 3)
+    x = net.input("data", N, 1, H, W, 4).sub(0, 3)            # 3 slices + a zero channel: 16-byte pixels
     feat, logits = dense_unet_2d(net, x, mode, skip)
     net.outputs["logits"] = logits
     net.outputs["feature"] = feat

@@ -167,9 +167,10 @@ int hdn_wce_grad(const float* logits, const float* labels, float* dlogits, int64
                  int64_t HW, int d0, int d1, const double* acc, float gscale, void* stream);
 
 /* Hybrid glue (hybridnet.py:385-396, 409-411).
- * triplets: vol (B,S,H,W) -> out (B*S,1,H,W,3), channel k of slice s = vol[clamp(s-1+k)].
+ * triplets: vol (B,S,H,W) -> out (B*S,1,H,W,ldc), channel k < 3 of slice s = vol[clamp(s-1+k)], channels
+ *           3..ldc-1 zero (ldc = 4 keeps pixels 16-byte aligned for the tensor-core stem).
  * cat4:     out (B,S,H,W,4) = [vol, 250*logits2d(3)];  cat4_bwd: dlogits += 250*dout[...,1:4]. */
-int hdn_triplets(const float* vol, float* out, int B, int S, int64_t HW, void* stream);
+int hdn_triplets(const float* vol, float* out, int B, int S, int64_t HW, int ldc, void* stream);
 int hdn_cat4(const float* vol, const float* logits, float* out, int64_t M, float k, void* stream);
 int hdn_cat4_bwd(const float* dout, float* dlogits, int64_t M, float k, int accumulate, void* stream);
 

@@ -137,7 +137,7 @@ def test_cuda_matches_torch_backend_same_device(cuda_dev):
         assert e < 1e-4, (b0.name, e)
     g0, g1 = ms[0].get_grads_dict(), ms[1].get_grads_dict()
     for k in g0:
-        if np.abs(g1[k]).max() < 1e-9:
+        if np.abs(g1[k]).max() < 1e-8:      # e.g. a bias in front of a training-mode BN: true gradient 0, pure rounding noise
             continue
         assert rel_l2(g0[k], g1[k]) < 5e-3, k
 

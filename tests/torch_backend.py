@@ -235,7 +235,9 @@ class TorchBackend(object):
         v = vol.view(B, S, HW)
         idx = torch.arange(S, device=vol.device)
         tri = torch.stack([(idx - 1).clamp(0, S - 1), idx, (idx + 1).clamp(0, S - 1)], dim=1)
-        out.view(B, S, HW, 3).copy_(v[:, tri].permute(0, 1, 3, 2))
+        o = out.view(B, S, HW, -1)
+        o.zero_()
+        o[..., :3].copy_(v[:, tri].permute(0, 1, 3, 2))
 
     def cat4(self, vol, logits, out, M, k):
         o = out.view(M, 4)

@@ -64,7 +64,7 @@ class DgradEpi(C.Structure):
 
 class Pool(C.Structure):
     _fields_ = [("kind", C.c_int), ("N", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int),
-                ("C", C.c_int), ("pool_d", C.c_int), ("src", Src), ("y", Tensor)]
+                ("C", C.c_int), ("pool_d", C.c_int), ("src", Src), ("y", Tensor), ("argidx", C.c_void_p)]
 
 
 class BnFold(C.Structure):

@@ -1,43 +1,50 @@
 // tcgen05 implicit-GEMM convolution path (precision == 1): bf16 operands, fp32 accumulation in
 // tensor memory.  Covers the stride-1 "same" convolutions of the dense blocks, transitions and
-// decoders: kernels 1x1x1, 1x3x3, 3x3x3 (hybridnet.py:264-298, 11-45, 235-260, 146-176) in
-// fprop and dgrad; everything the reference puts around them (BN -> Scale -> ReLU, ZeroPadding,
-// UpSampling, Add, bias, dropout, batch statistics, ReLU/BN backward sums) is fused into the
-// operand producer or the epilogue.
+// decoders: kernels 1x1x1, 1x3x3, 3x3x3 (hybridnet.py:264-298, 11-45, 235-260, 146-176) and the
+// stride-2 7x7(x7) stems in space-to-depth form, in fprop and dgrad; everything the reference
+// puts around them (BN -> Scale -> ReLU, ZeroPadding, UpSampling, Add, bias, dropout, batch
+// statistics, ReLU/BN backward sums) is fused into the operand producer or the epilogue.
 //
-// One CTA computes a 128 x BN output tile: 128 GEMM rows = 16 x 8 output pixels of one (n, d)
-// slice (or 128 consecutive positions for 1x1x1), BN <= 256 output channels.
+// Persistent kernel, one CTA per SM, each CTA loops over 128 x BN output tiles (128 GEMM rows =
+// 16 x 8 output pixels of one (n, d) slice, or 128 consecutive positions for 1x1x1).
 //
-//   warps 0-3  A producers: load the fp32 input PATCH (tile + halo, 18 x 10 pixels for a 3x3) once
-//              per 64-channel block, apply max(a*x+b, 0) (+ second source, + nearest-neighbour
-//              up-sampling in the index), convert to bf16 and store it in the UMMA no-swizzle
-//              K-major layout: chunk j (8 channels) at j*LBO, pixel q at q*16 bytes.  Every tap of
-//              the filter is then the SAME shared-memory patch read through a descriptor whose
-//              start address is shifted by (th*PW + tw)*16 bytes and whose 8-row-group stride is
-//              PW*16 bytes -- the im2col gather never happens and each input element is loaded
-//              once per tile instead of once per tap.  Afterwards the same warps run the epilogue.
-//   warp 4     weight loader: one elected thread streams pre-packed bf16 weight blocks
-//              (BN x 64, already in core-matrix order) with cp.async.bulk (TMA engine) on mbarriers.
-//   warp 5     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM and
-//              releases stages with tcgen05.commit.
+//   warps 0-3  producers.  Stage = one channel block (64, or 32 with two sources) of the fp32 input
+//              PATCH (tile + halo) of one depth slab.  The raw fp32 patch is fetched with cp.async
+//              (16-byte copies, several stages in flight, no registers held), then transformed once:
+//              max(a*x+b, 0) (+ second source, nearest-neighbour up-sampling in the index), bf16, stored
+//              in the UMMA no-swizzle K-major layout (chunk j of 8 channels at j*LBO, pixel q at q*16 B).
+//              Every filter tap is the SAME shared-memory patch read through a descriptor whose start
+//              address is shifted by (th*PW + tw)*16 bytes and whose 8-row-group stride is PW*16 bytes:
+//              no im2col gather, each input element is loaded once per tile instead of once per tap.
+//   warp 4     weight loader: one elected thread streams pre-packed bf16 weight blocks (already in
+//              core-matrix order) with cp.async.bulk (TMA engine) on mbarriers.
+//   warp 5     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
+//              TMEM accumulator buffers and releases stages with tcgen05.commit.
+//   warps 6-9  epilogue: tcgen05.ld the finished accumulator while the next tile's MMAs run.
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 192;
-constexpr int NSA = 3;        // A (activation patch) ring depth
-constexpr int NSB_MAX = 6;    // B (weight block) ring depth upper bound
-constexpr int UB = 4;         // producer: pixel groups loaded ahead per warp
+constexpr int TC_THREADS = 320;
+constexpr int NSA = 2;        // bf16 A-operand stages
+constexpr int NSB_MAX = 4;    // weight-block ring depth upper bound
+constexpr int NRAW_MAX = 4;   // raw fp32 patch ring depth upper bound
+constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs < NRAW_MAX tiles ahead of the transform)
+constexpr int UB = 4;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 
 struct TcParams {
   int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
   int kd, kh, kw;
   int K, NC;                  // contraction channels, output columns
-  int BN, KB, nsb, tmem_cols;
+  int BN, KB, CK, nsb, nraw, tmem_cols;
   int flat;                   // 1: rows are 128 consecutive linear positions (1x1x1, no up-sampling)
-  int PH, PW, P, Ppad;        // patch rows, cols, pixels, padded (odd) pixel count
+  int PH, PW, P, Ppad;        // virtual patch rows, cols, pixels, padded (odd) pixel count
+  int PHs[2], PWs[2], Ps[2];  // source-resolution patch of each source
+  int raw_off[2], ab_off[2], raw_bytes;   // layout of one raw stage
+  int tab_src[2], tab_vq[2], tab_ints;    // layout of one geometry table
   int tiles_w, tiles_h;
+  long long tiles, total_work;
   long long M;
   int nsrc;
   hdn_src src[2];             // A operand sources
@@ -61,71 +68,115 @@ struct TcParams {
   hdn_dgrad_epi epi[2];
 };
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+struct TileC { int n_tile, n_img, d0, h0, w0; long long m0; };
 
+__device__ __forceinline__ TileC tile_decode(const TcParams& p, long long w) {
+  TileC t;
+  t.n_tile = (int)(w / p.tiles);
+  long long r = w - (long long)t.n_tile * p.tiles;
+  t.n_img = t.d0 = t.h0 = t.w0 = 0; t.m0 = 0;
+  if (p.flat) {
+    t.m0 = r * 128;
+  } else {
+    const int tw_ = (int)(r % p.tiles_w); r /= p.tiles_w;
+    const int th_ = (int)(r % p.tiles_h); r /= p.tiles_h;
+    t.d0 = (int)(r % p.D); t.n_img = (int)(r / p.D);
+    t.h0 = th_ * 16; t.w0 = tw_ * 8;
+  }
+  return t;
+}
+
+// Iterator over the (work item, channel block, depth slab) stages of this CTA, in issue order.
+struct StageIt {
+  long long w;
+  int kb, dz, seq;
+  bool done;
+  TileC t;
+};
+__device__ __forceinline__ bool slab_ok(const TcParams& p, const StageIt& it) {
+  const int vd = it.t.d0 - p.pd_lo + it.dz;
+  return vd >= 0 && vd < p.D;
+}
+__device__ __forceinline__ void it_settle(const TcParams& p, StageIt& it) {   // move to the first valid stage at/after (kb, dz)
+  while (!it.done) {
+    if (it.dz >= p.kd) { it.dz = 0; ++it.kb; }
+    if (it.kb >= p.KB) {
+      it.w += gridDim.x; ++it.seq; it.kb = 0; it.dz = 0;
+      if (it.w >= p.total_work) { it.done = true; break; }
+      it.t = tile_decode(p, it.w);
+    }
+    if (slab_ok(p, it)) break;
+    ++it.dz;
+  }
+}
+__device__ __forceinline__ void it_init(const TcParams& p, StageIt& it) {
+  it.w = blockIdx.x; it.kb = 0; it.dz = 0; it.seq = 0;
+  it.done = it.w >= p.total_work;
+  if (!it.done) { it.t = tile_decode(p, it.w); it_settle(p, it); }
+}
+__device__ __forceinline__ void it_next(const TcParams& p, StageIt& it) { ++it.dz; it_settle(p, it); }
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 prologue4(float4 x, float4 a, float4 b, int relu) {
   float4 r;
   r.x = fmaf(a.x, x.x, b.x); r.y = fmaf(a.y, x.y, b.y); r.z = fmaf(a.z, x.z, b.z); r.w = fmaf(a.w, x.w, b.w);
   if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
   return r;
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait(int n) {     // n groups may remain in flight
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
+__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// Regroup the two channel quads a lane holds ([4*l8, +4) and [32 + 4*l8, +4)) with its neighbour lane into
+// 8-channel chunks and store the 16-byte chunk of pixel q.
+__device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q, bool qok, float4 v0, float4 v1, int lane) {
+  const int l8 = lane & 7;
+  const bool even = (l8 & 1) == 0;
+  const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
+  const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
+  const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+  const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
+  const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  uint4 o;
+  if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }     // chunk i      = [own quad A | partner quad A]
+  else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }     // chunk 4 + i  = [partner quad B | own quad B]
+  if (qok) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t A_BYTES = 8u * p.Ppad * 16u;
-  const uint32_t B_BYTES = (uint32_t)p.BN * 128u;
+  const uint32_t B_BYTES = (uint32_t)p.BN * (uint32_t)p.CK * 2u;
   uint8_t* sA = smem;
   uint8_t* sB = sA + NSA * A_BYTES;
-  int* pix = reinterpret_cast<int*>(sB + p.nsb * B_BYTES);          // [nsrc][P] in-slab element offsets, -1 = zero
-  float* sstat = reinterpret_cast<float*>(pix + 2 * p.P);           // [4][BN] column partial sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sstat + 4 * p.BN) + 15) & ~uintptr_t(15));
+  uint8_t* sRaw = sB + p.nsb * B_BYTES;
+  int* tabs = reinterpret_cast<int*>(sRaw + (size_t)p.nraw * p.raw_bytes);
+  float* sstat = reinterpret_cast<float*>(tabs + NTAB * p.tab_ints);        // [2 buffers][4][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 15) & ~uintptr_t(15));
   uint64_t* a_full = bars;
-  uint64_t* a_empty = bars + NSA;
-  uint64_t* b_full = bars + 2 * NSA;
-  uint64_t* b_empty = bars + 2 * NSA + NSB_MAX;
-  uint64_t* acc_full = bars + 2 * NSA + 2 * NSB_MAX;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* a_empty = a_full + NSA;
+  uint64_t* b_full = a_empty + NSA;
+  uint64_t* b_empty = b_full + NSB_MAX;
+  uint64_t* acc_full = b_empty + NSB_MAX;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  // ---- tile coordinates
-  const int n_tile = blockIdx.y;
-  int n_img = 0, d0 = 0, h0 = 0, w0 = 0;
-  long long m0 = 0;
-  if (p.flat) {
-    m0 = (long long)blockIdx.x * 128;
-  } else {
-    int t = blockIdx.x;
-    const int tw_ = t % p.tiles_w; t /= p.tiles_w;
-    const int th_ = t % p.tiles_h; t /= p.tiles_h;
-    d0 = t % p.D; n_img = t / p.D;
-    h0 = th_ * 16; w0 = tw_ * 8;
-  }
-  const int hh = p.ph_lo, hw = p.pw_lo, hd = p.pd_lo;
-
-  // ---- one-time setup
-  for (int i = tid; i < p.nsrc * p.P; i += TC_THREADS) {
-    const int s = i / p.P, q = i - s * p.P;
-    const hdn_src& S = p.src[s];
-    int off = -1;
-    if (p.flat) {
-      if (m0 + q < p.M) off = q * S.t.ldc;
-    } else {
-      const int vh = h0 - hh + q / p.PW, vw = w0 - hw + q % p.PW;
-      if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
-        if (p.s2d) off = (2 * vh * S.W + 2 * vw) * S.t.ldc;
-        else {
-          const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
-          off = (sh * S.W + sw) * S.t.ldc;
-        }
-      }
-    }
-    pix[i] = off;
-  }
-  for (int i = tid; i < 4 * p.BN; i += TC_THREADS) sstat[i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < NSA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB_MAX; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
   }
   if (warp == 5) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -139,348 +190,493 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 
   if (warp < 4) {
     // =================================================================== A producers
+    const int ptid = tid;                                 // 0..127
     const int l8 = lane & 7, pg = lane >> 3;
-    const bool even = (l8 & 1) == 0;
-    const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
-    int sa = 0;
-    uint32_t pha = 0;
-    for (int kb = 0; kb < p.KB; ++kb) {
-      const int c0 = kb * 64;
-      const int cA = c0 + l8 * 4, cB = c0 + 32 + l8 * 4;       // this lane's two channel quads
-      bool okA = cA < p.K, okB = cB < p.K;                     // K % 8 == 0, so a quad is all-in or all-out
-      int s2d_rd = 0, s2d_add = 0;
-      if (p.s2d) {                                             // quad l8 = (rd, rh, rw): 8 floats (rw, c) are contiguous in x
-        okA = l8 < p.s2d_quads; okB = false;
-        s2d_rd = (p.s2d_quads == 8) ? (l8 >> 2) : 0;
-        s2d_add = ((l8 >> 1) & 1) * p.src[0].W * p.src[0].t.ldc + (l8 & 1) * 4 - cA;   // "- cA": the generic code adds cA
-      }
-      float4 a0[2], b0[2], a1[2], b1[2];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
-        b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < p.nsrc) {
-          const hdn_src& S = p.src[s];
-          if (S.pa) { if (okA) a0[s] = ldg4(S.pa + cA); if (okB) a1[s] = ldg4(S.pa + cB); }
-          if (S.pb) { if (okA) b0[s] = ldg4(S.pb + cA); if (okB) b1[s] = ldg4(S.pb + cB); }
+    int built_seq = -1;
+
+    // geometry tables of a tile: per source, [Ps] source-patch pixel -> element offset in the slab (or -1),
+    // and [P] virtual patch pixel -> source-patch pixel index (or -1 => zero padding)
+    auto build_tables = [&](const StageIt& it) {
+      int* tab = tabs + (it.seq % NTAB) * p.tab_ints;
+      const TileC& t = it.t;
+      for (int s = 0; s < p.nsrc; ++s) {
+        const hdn_src& S = p.src[s];
+        const int vh0 = t.h0 - p.ph_lo, vw0 = t.w0 - p.pw_lo;
+        const int sh0 = (S.uh == 2) ? (vh0 >> 1) : vh0, sw0 = (S.uw == 2) ? (vw0 >> 1) : vw0;
+        for (int i = ptid; i < p.Ps[s]; i += 128) {
+          int off = -1;
+          if (p.flat) {
+            if (t.m0 + i < p.M) off = i * S.t.ldc;
+          } else {
+            const int sh = sh0 + i / p.PWs[s], sw = sw0 + i % p.PWs[s];
+            const int hlim = p.s2d ? p.H : S.H, wlim = p.s2d ? p.W : S.W;      // s2d: the patch lives on the half-resolution grid
+            if (sh >= 0 && sh < hlim && sw >= 0 && sw < wlim) off = p.s2d ? (2 * sh * S.W + 2 * sw) * S.t.ldc : (sh * S.W + sw) * S.t.ldc;
+          }
+          tab[p.tab_src[s] + i] = off;
         }
-      }
-      for (int dz = 0; dz < p.kd; ++dz) {
-        const int vd = d0 - hd + dz;
-        if (vd < 0 || vd >= p.D) continue;
-        const float* base[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          base[s] = nullptr;
-          if (s < p.nsrc) {
-            const hdn_src& S = p.src[s];
-            if (p.flat) {
-              base[s] = S.t.p + m0 * S.t.ldc + S.t.coff;
-            } else if (p.s2d) {
-              base[s] = S.t.p + ((long long)n_img * S.D + (p.s2d_quads == 8 ? 2 * vd + s2d_rd : vd)) * S.H * S.W * S.t.ldc + S.t.coff + s2d_add;
-            } else {
-              const int sd = (S.ud == 2) ? (vd >> 1) : vd;
-              base[s] = S.t.p + ((long long)n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+        for (int q = ptid; q < p.P; q += 128) {
+          int sq = -1;
+          if (p.flat) {
+            if (t.m0 + q < p.M) sq = q;
+          } else {
+            const int vh = vh0 + q / p.PW, vw = vw0 + q % p.PW;
+            if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
+              const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
+              sq = (sh - sh0) * p.PWs[s] + (sw - sw0);
             }
           }
+          tab[p.tab_vq[s] + q] = sq;
         }
+      }
+      bar_producers();
+    };
+    auto slab_base = [&](const StageIt& it, int s) -> const float* {
+      const hdn_src& S = p.src[s];
+      if (p.flat) return S.t.p + it.t.m0 * S.t.ldc + S.t.coff;
+      const int vd = it.t.d0 - p.pd_lo + it.dz;
+      const int sd = (S.ud == 2) ? (vd >> 1) : vd;
+      return S.t.p + ((long long)it.t.n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+    };
+
+    StageIt tr;
+    it_init(p, tr);
+    int sa = 0;
+    uint32_t pha = 0;
+
+    if (!p.s2d) {
+      // ---- asynchronous path: raw fp32 patch -> shared memory with cp.async, several stages ahead
+      StageIt is;
+      it_init(p, is);
+      const int NQ = p.CK >> 2;                            // 16-byte quads per pixel in a raw stage
+      auto issue = [&](const StageIt& it, int slot) {
+        if (it.seq != built_seq) { build_tables(it); built_seq = it.seq; }
+        const int* tab = tabs + (it.seq % NTAB) * p.tab_ints;
+        uint8_t* raw = sRaw + (size_t)slot * p.raw_bytes;
+        const int c0 = it.kb * p.CK;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const hdn_src& S = p.src[s];
+          const float* base = slab_base(it, s);
+          const int* spix = tab + p.tab_src[s];
+          uint8_t* rs = raw + p.raw_off[s];
+          const int n16 = p.Ps[s] * NQ;
+          for (int i = ptid; i < n16; i += 128) {
+            const int sq = i / NQ, part = i - sq * NQ;
+            const int off = spix[sq], c = c0 + part * 4;
+            if (off >= 0 && c < p.K) cp_async16(rs + (size_t)i * 16, base + off + c);
+          }
+          if (ptid < NQ && c0 + ptid * 4 < p.K) {
+            if (S.pa) cp_async16(raw + p.ab_off[s] + ptid * 16, S.pa + c0 + ptid * 4);
+            if (S.pb) cp_async16(raw + p.ab_off[s] + p.CK * 4 + ptid * 16, S.pb + c0 + ptid * 4);
+          }
+        }
+      };
+      int slot_is = 0, slot_tr = 0;
+      for (int i = 0; i < p.nraw - 1; ++i) {
+        if (!is.done) { issue(is, slot_is); it_next(p, is); }
+        cp_async_commit();
+        if (++slot_is == p.nraw) slot_is = 0;
+      }
+      while (!tr.done) {
+        cp_async_wait(p.nraw - 2);                         // this thread's copies of stage `tr` have landed
+        bar_producers();                                   // ... and everyone else's; everyone is also done reading the slot refilled next
+        if (!is.done) { issue(is, slot_is); it_next(p, is); }
+        cp_async_commit();
+        if (++slot_is == p.nraw) slot_is = 0;
         tc::mbar_wait(&a_empty[sa], pha ^ 1);
-        uint8_t* dst = sA + sa * A_BYTES;
-        // UB pixel groups per warp are loaded before any is used: the loads of a batch are all in flight
-        // together (memory-level parallelism is what bounds this producer, not instruction count)
-        for (int q0 = warp * 4; q0 < p.P; q0 += 16 * UB) {
-          float4 r0[UB][2], r1[UB][2];
-          bool inb[UB][2];
+        {
+          const int* tab = tabs + (tr.seq % NTAB) * p.tab_ints;
+          const uint8_t* raw = sRaw + (size_t)slot_tr * p.raw_bytes;
+          uint8_t* dst = sA + sa * A_BYTES;
+          const int c0 = tr.kb * p.CK;
+          const int cA = l8 * 4, cB = 32 + l8 * 4;         // channel quads of this lane inside the stage
+          const bool okA = cA < p.CK && c0 + cA < p.K, okB = cB < p.CK && c0 + cB < p.K;
+          float4 a0[2], b0[2], a1[2], b1[2];
 #pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            const int q = q0 + u * 16 + pg;
+          for (int s = 0; s < 2; ++s) {
+            a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
+            b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < p.nsrc) {
+              const float* ab = reinterpret_cast<const float*>(raw + p.ab_off[s]);
+              if (p.src[s].pa) { if (okA) a0[s] = *reinterpret_cast<const float4*>(ab + cA); if (okB) a1[s] = *reinterpret_cast<const float4*>(ab + cB); }
+              if (p.src[s].pb) { if (okA) b0[s] = *reinterpret_cast<const float4*>(ab + p.CK + cA); if (okB) b1[s] = *reinterpret_cast<const float4*>(ab + p.CK + cB); }
+            }
+          }
+          for (int q0 = warp * 4; q0 < p.P; q0 += 16) {
+            const int q = q0 + pg;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (q < p.P) {
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              inb[u][s] = false;
-              r0[u][s] = r1[u][s] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (s < p.nsrc && q < p.P) {
-                const int off = pix[s * p.P + q];
-                if (off >= 0) {
-                  inb[u][s] = true;
-                  const float* g = base[s] + off;
-                  if (okA) r0[u][s] = ldg4(g + cA);
-                  if (okB) r1[u][s] = ldg4(g + cB);
+              for (int s = 0; s < 2; ++s) {
+                if (s < p.nsrc) {
+                  const int sq = tab[p.tab_vq[s] + q];
+                  const int off = sq >= 0 ? tab[p.tab_src[s] + sq] : -1;      // zero padding is applied AFTER BN/Scale/ReLU
+                  if (off >= 0) {
+                    const float* row = reinterpret_cast<const float*>(raw + p.raw_off[s]) + (size_t)sq * p.CK;
+                    const int relu = p.src[s].relu;
+                    if (okA) { float4 t = prologue4(*reinterpret_cast<const float4*>(row + cA), a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
+                    if (okB) { float4 t = prologue4(*reinterpret_cast<const float4*>(row + cB), a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
+                  }
                 }
               }
             }
-          }
-#pragma unroll
-          for (int u = 0; u < UB; ++u) {
-            if (q0 + u * 16 >= p.P) break;                       // warp-uniform
-            const int q = q0 + u * 16 + pg;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              if (s < p.nsrc && inb[u][s]) {                     // zero padding is applied AFTER BN/Scale/ReLU
-                const int relu = p.src[s].relu;
-                if (okA) { float4 t = prologue4(r0[u][s], a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
-                if (okB) { float4 t = prologue4(r1[u][s], a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
-              }
-            }
-            // lanes (2i, 2i+1) hold channels [8i,8i+4) / [8i+4,8i+8) and [32+8i,..): regroup into 8-channel chunks
-            const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
-            const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
-            const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
-            const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-            uint4 o;
-            if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }     // chunk i      = [own quad A | partner quad A]
-            else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }     // chunk 4 + i  = [partner quad B | own quad B]
-            if (q < p.P) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * p.Ppad * 16u + (uint32_t)q * 16u) = o;
+            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, v0, v1, lane);
           }
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[sa]);
         if (++sa == NSA) { sa = 0; pha ^= 1; }
-      }
-    }
-
-    // =================================================================== epilogue
-    tc::mbar_wait(acc_full, 0);
-    tc::tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int hr = row >> 3, wr = row & 7;
-    bool rvalid;
-    long long m;
-    int oh = 0, ow = 0;
-    if (p.flat) {
-      m = m0 + row;
-      rvalid = m < p.M;
-    } else {
-      oh = h0 + hr; ow = w0 + wr;
-      rvalid = oh < p.H && ow < p.W;
-      m = (((long long)n_img * p.D + d0) * p.H + oh) * p.W + ow;
-    }
-    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    float v[16];
-
-    if (p.mode == 0) {
-      const bool do_stats = p.stat_sum != nullptr;
-      const bool vec = (p.NC % 4 == 0) && (p.y.ldc % 4 == 0) && (p.y.coff % 4 == 0) &&
-                       ((reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0);
-      float* yrow = const_cast<float*>(p.y.p) + m * p.y.ldc + p.y.coff;
-      for (int cc = 0; cc < p.BN; cc += 16) {
-        tc::tmem_ld16(taddr + cc, v);
-        const int col0 = n_tile * p.BN + cc;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = col0 + i;
-          float t = v[i];
-          if (col < p.NC) {
-            if (p.bias) t += __ldg(p.bias + col);
-            if (p.drop_keep < 1.0f) t *= hdn_drop_scale(p.drop_seed, (uint64_t)m * p.NC + col, p.drop_keep);
-          }
-          v[i] = t;
-        }
-        if (rvalid) {
-          if (vec) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              if (col0 + i < p.NC) *reinterpret_cast<float4*>(yrow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (col0 + i < p.NC) yrow[col0 + i] = v[i];
-          }
-        }
-        if (do_stats) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float s = rvalid ? v[i] : 0.f;
-            float q2 = s * s;
-            s = warp_sum(s); q2 = warp_sum(q2);
-            if (lane == i) { atomicAdd(&sstat[cc + i], s); atomicAdd(&sstat[p.BN + cc + i], q2); }
-          }
-        }
-      }
-      if (do_stats) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = tid; c < p.BN; c += 128) {
-          const int col = n_tile * p.BN + c;
-          if (col < p.NC) {
-            atomicAdd(p.stat_sum + col, (double)sstat[c]);
-            atomicAdd(p.stat_sq + col, (double)sstat[p.BN + c]);
-          }
-        }
-      }
-    } else if (p.scatter) {
-      // dgrad of a stride-2 stem in space-to-depth form: column (rd,rh,rw,c) of s2d pixel (d0,oh,ow) is the
-      // gradient of x[2*d0+rd][2*oh+rh][2*ow+rw][c]; the input has no prologue (hybridnet.py:122-123,208-209)
-      const hdn_dgrad_epi& E = p.epi[0];
-      const hdn_src& S = p.esrc[0];
-      for (int cc = 0; cc < p.BN; cc += 16) {
-        tc::tmem_ld16(taddr + cc, v);
-        if (!rvalid) continue;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const int qd = (n_tile * p.BN + cc + i) >> 2;
-          if (qd >= p.s2d_quads) continue;
-          const int rd = (p.s2d_quads == 8) ? (qd >> 2) : 0, rh = (qd >> 1) & 1, rw = qd & 1;
-          const int sd = (p.s2d_quads == 8) ? (2 * d0 + rd) : d0;
-          const long long ms = (((long long)n_img * S.D + sd) * S.H + 2 * oh + rh) * S.W + 2 * ow + rw;
-          float* q = const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff;
-          float4 g = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
-          *reinterpret_cast<float4*>(q) = g;
-        }
+        if (++slot_tr == p.nraw) slot_tr = 0;
+        it_next(p, tr);
       }
     } else {
-      // dgrad: v = dz at a (virtual-resolution) input position; per source: reduce the up-sampling
-      // sub-positions, ReLU mask from the stored value, S1/S2 sums, then dx (+)= a*du or du (+)= du.
-      for (int cc = 0; cc < p.BN; cc += 16) {
-        tc::tmem_ld16(taddr + cc, v);
-        const int col0 = n_tile * p.BN + cc;
-        for (int e = 0; e < p.nepi; ++e) {
-          const hdn_dgrad_epi& E = p.epi[e];
-          if (E.mode == 2) continue;
-          const hdn_src& S = p.esrc[e];
-          long long ms = m;
-          bool writer = rvalid;
-          if (!p.flat) {
-            const int sd = (S.ud == 2) ? (d0 >> 1) : d0, sh = (S.uh == 2) ? (oh >> 1) : oh, sw = (S.uw == 2) ? (ow >> 1) : ow;
-            ms = (((long long)n_img * S.D + sd) * S.H + sh) * S.W + sw;
-            if (S.uw == 2 && (wr & 1)) writer = false;
-            if (S.uh == 2 && (hr & 1)) writer = false;
+      // ---- direct path (space-to-depth stems): register loads, UB pixel groups in flight per warp
+      const bool okA = l8 < p.s2d_quads;
+      const hdn_src& S = p.src[0];
+      const int s2d_rd = (p.s2d_quads == 8) ? (l8 >> 2) : 0;
+      const int s2d_add = ((l8 >> 1) & 1) * S.W * S.t.ldc + (l8 & 1) * 4;     // quad l8 = (rd, rh, rw): (rw, c) contiguous in x
+      while (!tr.done) {
+        if (tr.seq != built_seq) { build_tables(tr); built_seq = tr.seq; }
+        const int* tab = tabs + (tr.seq % NTAB) * p.tab_ints;
+        const int vd = tr.t.d0 - p.pd_lo + tr.dz;
+        const float* base = S.t.p + ((long long)tr.t.n_img * S.D + (p.s2d_quads == 8 ? 2 * vd + s2d_rd : vd)) * S.H * S.W * S.t.ldc +
+                            S.t.coff + s2d_add;
+        tc::mbar_wait(&a_empty[sa], pha ^ 1);
+        uint8_t* dst = sA + sa * A_BYTES;
+        for (int q0 = warp * 4; q0 < p.P; q0 += 16 * UB) {
+          float4 r0[UB];
+#pragma unroll
+          for (int u = 0; u < UB; ++u) {
+            const int q = q0 + u * 16 + pg;
+            r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < p.P && okA) {
+              const int sq = tab[p.tab_vq[0] + q];
+              const int off = sq >= 0 ? tab[p.tab_src[0] + sq] : -1;
+              if (off >= 0) r0[u] = ldg4(base + off);
+            }
           }
-          const bool atom = (S.ud == 2);
-          const float* xrow = S.t.p + ms * S.t.ldc + S.t.coff;
-          const bool do_s = E.s1 != nullptr;
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float dz[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float t = rvalid ? v[i + j] : 0.f;
-              if (S.uw == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
-              if (S.uh == 2) t += __shfl_xor_sync(0xffffffffu, t, 8);
-              dz[j] = t;
-            }
-            const int col = col0 + i;
-            const bool cok = col < p.NC;          // NC % 4 == 0 on this path
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), a = make_float4(1.f, 1.f, 1.f, 1.f), b = x, ctr = x;
-            if (cok) {
-              if (writer) x = ldg4(xrow + col);
-              if (S.pa) a = ldg4(S.pa + col);
-              if (S.pb) b = ldg4(S.pb + col);
-              if (do_s && E.center) ctr = ldg4(E.center + col);
-            }
-            const float xa[4] = {x.x, x.y, x.z, x.w}, aa[4] = {a.x, a.y, a.z, a.w}, ba[4] = {b.x, b.y, b.z, b.w},
-                        ca[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
-            float du[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float t = (writer && cok) ? dz[j] : 0.f;
-              if (S.relu && !(fmaf(aa[j], xa[j], ba[j]) > 0.f)) t = 0.f;
-              du[j] = t;
-            }
-            if (do_s) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float s1 = warp_sum(du[j]);
-                float s2 = warp_sum(du[j] * (xa[j] - ca[j]));
-                if (lane == i + j) { atomicAdd(&sstat[(2 * e) * p.BN + cc + i + j], s1); atomicAdd(&sstat[(2 * e + 1) * p.BN + cc + i + j], s2); }
-              }
-            }
-            if (writer && cok) {
-              if (E.mode == 0) {
-                float* q = const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff + col;
-                float4 g = make_float4(aa[0] * du[0], aa[1] * du[1], aa[2] * du[2], aa[3] * du[3]);
-                if (atom) { atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w); }
-                else {
-                  if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
-                  *reinterpret_cast<float4*>(q) = g;
-                }
-              } else {
-                float* q = E.du + ms * p.NC + col;
-                float4 g = make_float4(du[0], du[1], du[2], du[3]);
-                if (atom) { atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w); }
-                else {
-                  if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
-                  *reinterpret_cast<float4*>(q) = g;
-                }
-              }
-            }
+          for (int u = 0; u < UB; ++u) {
+            if (q0 + u * 16 >= p.P) break;                  // warp-uniform
+            const int q = q0 + u * 16 + pg;
+            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, r0[u], make_float4(0.f, 0.f, 0.f, 0.f), lane);
           }
         }
-      }
-      bool any_s = false;
-      for (int e = 0; e < p.nepi; ++e) any_s = any_s || (p.epi[e].mode != 2 && p.epi[e].s1 != nullptr);
-      if (any_s) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int e = 0; e < p.nepi; ++e) {
-          const hdn_dgrad_epi& E = p.epi[e];
-          if (E.mode == 2 || E.s1 == nullptr) continue;
-          for (int c = tid; c < p.BN; c += 128) {
-            const int col = n_tile * p.BN + c;
-            if (col < p.NC) {
-              const float s1 = sstat[(2 * e) * p.BN + c], s2 = sstat[(2 * e + 1) * p.BN + c];
-              if (s1 != 0.f) atomicAdd(E.s1 + col, (double)s1);
-              if (s2 != 0.f) atomicAdd(E.s2 + col, (double)s2);
-            }
-          }
-        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&a_full[sa]);
+        if (++sa == NSA) { sa = 0; pha ^= 1; }
+        it_next(p, tr);
       }
     }
   } else if (warp == 4) {
     // =================================================================== weight loader (TMA engine)
     if (lane == 0) {
-      const __nv_bfloat16* wp = p.wpack + (size_t)n_tile * p.KB * T * ((size_t)p.BN * 64);
+      StageIt it;
+      it_init(p, it);
       int sb = 0;
       uint32_t phb = 0;
-      for (int kb = 0; kb < p.KB; ++kb)
-        for (int dz = 0; dz < p.kd; ++dz) {
-          const int vd = d0 - hd + dz;
-          if (vd < 0 || vd >= p.D) continue;
-          for (int t2 = 0; t2 < taps_hw; ++t2) {
-            const int tap = dz * taps_hw + t2;
-            tc::mbar_wait(&b_empty[sb], phb ^ 1);
-            tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
-            tc::bulk_g2s(sB + sb * B_BYTES, wp + ((size_t)kb * T + tap) * ((size_t)p.BN * 64), B_BYTES, &b_full[sb]);
-            if (++sb == p.nsb) { sb = 0; phb ^= 1; }
-          }
+      const size_t blk = (size_t)p.BN * p.CK;
+      while (!it.done) {
+        const __nv_bfloat16* wp = p.wpack + (size_t)it.t.n_tile * p.KB * T * blk;
+        for (int t2 = 0; t2 < taps_hw; ++t2) {
+          const int tap = it.dz * taps_hw + t2;
+          tc::mbar_wait(&b_empty[sb], phb ^ 1);
+          tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+          tc::bulk_g2s(sB + sb * B_BYTES, wp + ((size_t)it.kb * T + tap) * blk, B_BYTES, &b_full[sb]);
+          if (++sb == p.nsb) { sb = 0; phb ^= 1; }
         }
+        it_next(p, it);
+      }
     }
-  } else {
+  } else if (warp == 5) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 0, 0);
       const uint32_t lbo_a = (uint32_t)p.Ppad * 16u, sbo_a = (uint32_t)p.PW * 16u;
       const uint32_t lbo_b = (uint32_t)p.BN * 16u, sbo_b = 128u;
+      StageIt it;
+      it_init(p, it);
       int sa = 0, sb = 0;
-      uint32_t pha = 0, phb = 0, acc = 0;
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int cv = min(64, p.K - kb * 64);
-        const int nk = (cv + 15) >> 4;
-        for (int dz = 0; dz < p.kd; ++dz) {
-          const int vd = d0 - hd + dz;
-          if (vd < 0 || vd >= p.D) continue;
-          tc::mbar_wait(&a_full[sa], pha);
+      uint32_t pha = 0, phb = 0;
+      int cur_seq = -1;
+      uint32_t acc = 0, tmem_d = tmem_base;
+      while (!it.done) {
+        if (it.seq != cur_seq) {                            // first stage of a new tile: claim an accumulator buffer
+          cur_seq = it.seq;
+          const int ab = cur_seq & 1;
+          tc::mbar_wait(&acc_empty[ab], ((uint32_t)(cur_seq >> 1) & 1u) ^ 1u);
           tc::tc_fence_after();
-          const uint32_t a_stage = tc::smem_u32(sA + sa * A_BYTES);
-          for (int t2 = 0; t2 < taps_hw; ++t2) {
-            const int th = t2 / p.kw, tw = t2 - th * p.kw;
-            tc::mbar_wait(&b_full[sb], phb);
-            tc::tc_fence_after();
-            const uint32_t a_base = a_stage + (uint32_t)(th * p.PW + tw) * 16u;
-            const uint32_t b_base = tc::smem_u32(sB + sb * B_BYTES);
-            for (int k = 0; k < nk; ++k) {
-              const uint64_t ad = tc::make_smem_desc(a_base + (uint32_t)k * 2u * lbo_a, lbo_a, sbo_a);
-              const uint64_t bd = tc::make_smem_desc(b_base + (uint32_t)k * 2u * lbo_b, lbo_b, sbo_b);
-              tc::umma_bf16(tmem_base, ad, bd, idesc, acc);
-              acc = 1;
-            }
-            tc::umma_commit(&b_empty[sb]);
-            if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+          tmem_d = tmem_base + (uint32_t)(ab * p.BN);
+          acc = 0;
+        }
+        const int cv = min(p.CK, p.K - it.kb * p.CK);
+        const int nk = (cv + 15) >> 4;
+        tc::mbar_wait(&a_full[sa], pha);
+        tc::tc_fence_after();
+        const uint32_t a_stage = tc::smem_u32(sA + sa * A_BYTES);
+        for (int t2 = 0; t2 < taps_hw; ++t2) {
+          const int th = t2 / p.kw, tw = t2 - th * p.kw;
+          tc::mbar_wait(&b_full[sb], phb);
+          tc::tc_fence_after();
+          const uint32_t a_base = a_stage + (uint32_t)(th * p.PW + tw) * 16u;
+          const uint32_t b_base = tc::smem_u32(sB + sb * B_BYTES);
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = tc::make_smem_desc(a_base + (uint32_t)k * 2u * lbo_a, lbo_a, sbo_a);
+            const uint64_t bd = tc::make_smem_desc(b_base + (uint32_t)k * 2u * lbo_b, lbo_b, sbo_b);
+            tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
+            acc = 1;
           }
-          tc::umma_commit(&a_empty[sa]);
-          if (++sa == NSA) { sa = 0; pha ^= 1; }
+          tc::umma_commit(&b_empty[sb]);
+          if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+        }
+        tc::umma_commit(&a_empty[sa]);
+        if (++sa == NSA) { sa = 0; pha ^= 1; }
+        const int seq_before = it.seq;
+        it_next(p, it);
+        if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
+      }
+    }
+  } else {
+    // =================================================================== epilogue (warps 6-9)
+    const int etid = tid - 192;                             // 0..127
+    const int qtr = warp & 3;                               // TMEM lane quarter this warp may read
+    const int row = qtr * 32 + lane;
+    const int hr = row >> 3, wr = row & 7;
+    int seq = 0;
+    float v[16];
+    for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++seq) {
+      const TileC t = tile_decode(p, w);
+      const int ab = seq & 1;
+      float* st_ = sstat + ab * 4 * p.BN;
+      const int n_tile = t.n_tile;
+      bool rvalid;
+      long long m;
+      int oh = 0, ow = 0;
+      if (p.flat) {
+        m = t.m0 + row;
+        rvalid = m < p.M;
+      } else {
+        oh = t.h0 + hr; ow = t.w0 + wr;
+        rvalid = oh < p.H && ow < p.W;
+        m = (((long long)t.n_img * p.D + t.d0) * p.H + oh) * p.W + ow;
+      }
+      bool any_s = false;
+      if (p.mode == 0) any_s = p.stat_sum != nullptr;
+      else if (!p.scatter)
+        for (int e = 0; e < p.nepi; ++e) any_s = any_s || (p.epi[e].mode != 2 && p.epi[e].s1 != nullptr);
+      if (any_s) {
+        for (int i = etid; i < 4 * p.BN; i += 128) st_[i] = 0.f;
+        bar_epilogue();
+      }
+      tc::mbar_wait(&acc_full[ab], (uint32_t)(seq >> 1) & 1u);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * p.BN);
+
+      if (p.mode == 0) {
+        const bool do_stats = p.stat_sum != nullptr;
+        const bool vec = (p.NC % 4 == 0) && (p.y.ldc % 4 == 0) && (p.y.coff % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0);
+        float* yrow = const_cast<float*>(p.y.p) + m * p.y.ldc + p.y.coff;
+        for (int cc = 0; cc < p.BN; cc += 16) {
+          tc::tmem_ld16(taddr + cc, v);
+          const int col0 = n_tile * p.BN + cc;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int col = col0 + i;
+            float tv = v[i];
+            if (col < p.NC) {
+              if (p.bias) tv += __ldg(p.bias + col);
+              if (p.drop_keep < 1.0f) tv *= hdn_drop_scale(p.drop_seed, (uint64_t)m * p.NC + col, p.drop_keep);
+            }
+            v[i] = tv;
+          }
+          if (rvalid) {
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                if (col0 + i < p.NC) *reinterpret_cast<float4*>(yrow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (col0 + i < p.NC) yrow[col0 + i] = v[i];
+            }
+          }
+          if (do_stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float s = rvalid ? v[i] : 0.f;
+              float q2 = s * s;
+              s = warp_sum(s); q2 = warp_sum(q2);
+              if (lane == i) { atomicAdd(&st_[cc + i], s); atomicAdd(&st_[p.BN + cc + i], q2); }
+            }
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&acc_empty[ab]);                   // accumulator buffer may be overwritten
+        if (do_stats) {
+          bar_epilogue();
+          for (int c = etid; c < p.BN; c += 128) {
+            const int col = n_tile * p.BN + c;
+            if (col < p.NC) {
+              atomicAdd(p.stat_sum + col, (double)st_[c]);
+              atomicAdd(p.stat_sq + col, (double)st_[p.BN + c]);
+            }
+          }
+        }
+      } else if (p.scatter) {
+        // dgrad of a stride-2 stem in space-to-depth form: column (rd,rh,rw,c) of s2d pixel (d0,oh,ow) is the
+        // gradient of x[2*d0+rd][2*oh+rh][2*ow+rw][c]; the input has no prologue (hybridnet.py:122-123,208-209)
+        const hdn_dgrad_epi& E = p.epi[0];
+        const hdn_src& S = p.esrc[0];
+        for (int cc = 0; cc < p.BN; cc += 16) {
+          tc::tmem_ld16(taddr + cc, v);
+          if (!rvalid) continue;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const int qd = (n_tile * p.BN + cc + i) >> 2;
+            if (qd >= p.s2d_quads) continue;
+            const int rd = (p.s2d_quads == 8) ? (qd >> 2) : 0, rh = (qd >> 1) & 1, rw = qd & 1;
+            const int sd = (p.s2d_quads == 8) ? (2 * t.d0 + rd) : t.d0;
+            const long long ms = (((long long)t.n_img * S.D + sd) * S.H + 2 * oh + rh) * S.W + 2 * ow + rw;
+            float* q = const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff;
+            float4 g = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (E.accumulate) { float4 o = *reinterpret_cast<float4*>(q); g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+            *reinterpret_cast<float4*>(q) = g;
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&acc_empty[ab]);
+      } else {
+        // dgrad: v = dz at a (virtual-resolution) input position; per source: reduce the up-sampling
+        // sub-positions, ReLU mask from the stored value, S1/S2 sums, then dx (+)= a*du or du (+)= du.
+        // The stored value x and (when accumulating) the old gradient of the NEXT column chunk are requested
+        // before the current chunk is processed: the epilogue is a stream of dependent global loads otherwise.
+        const bool pf = p.nepi == 1 && p.epi[0].mode != 2;
+        float4 xn[4], on[4];
+        long long ms0 = m;
+        bool writer0 = rvalid;
+        const float* xrow0 = nullptr;
+        float* orow0 = nullptr;
+        bool rmw0 = false;
+        if (pf) {
+          const hdn_src& S = p.esrc[0];
+          const hdn_dgrad_epi& E = p.epi[0];
+          if (!p.flat) {
+            const int sd = (S.ud == 2) ? (t.d0 >> 1) : t.d0, sh = (S.uh == 2) ? (oh >> 1) : oh, sw = (S.uw == 2) ? (ow >> 1) : ow;
+            ms0 = (((long long)t.n_img * S.D + sd) * S.H + sh) * S.W + sw;
+            if (S.uw == 2 && (wr & 1)) writer0 = false;
+            if (S.uh == 2 && (hr & 1)) writer0 = false;
+          }
+          xrow0 = S.t.p + ms0 * S.t.ldc + S.t.coff;
+          rmw0 = E.accumulate && S.ud != 2;
+          orow0 = E.mode == 0 ? const_cast<float*>(E.dx.p) + ms0 * E.dx.ldc + E.dx.coff : E.du + ms0 * p.NC;
+        }
+        auto prefetch = [&](int cc) {
+          const int col0 = n_tile * p.BN + cc;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            xn[i] = on[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (writer0 && col0 + 4 * i < p.NC) {
+              xn[i] = ldg4(xrow0 + col0 + 4 * i);
+              if (rmw0) on[i] = *reinterpret_cast<const float4*>(orow0 + col0 + 4 * i);
+            }
+          }
+        };
+        if (pf) prefetch(0);
+        for (int cc = 0; cc < p.BN; cc += 16) {
+          float4 xc[4], oc[4];
+          if (pf) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { xc[i] = xn[i]; oc[i] = on[i]; }
+            if (cc + 16 < p.BN) prefetch(cc + 16);
+          }
+          tc::tmem_ld16(taddr + cc, v);
+          const int col0 = n_tile * p.BN + cc;
+          for (int e = 0; e < p.nepi; ++e) {
+            const hdn_dgrad_epi& E = p.epi[e];
+            if (E.mode == 2) continue;
+            const hdn_src& S = p.esrc[e];
+            long long ms = m;
+            bool writer = rvalid;
+            if (!p.flat) {
+              const int sd = (S.ud == 2) ? (t.d0 >> 1) : t.d0, sh = (S.uh == 2) ? (oh >> 1) : oh, sw = (S.uw == 2) ? (ow >> 1) : ow;
+              ms = (((long long)t.n_img * S.D + sd) * S.H + sh) * S.W + sw;
+              if (S.uw == 2 && (wr & 1)) writer = false;
+              if (S.uh == 2 && (hr & 1)) writer = false;
+            }
+            const bool atom = (S.ud == 2);
+            const float* xrow = S.t.p + ms * S.t.ldc + S.t.coff;
+            const bool do_s = E.s1 != nullptr;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float dz[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float tv = rvalid ? v[i + j] : 0.f;
+                if (S.uw == 2) tv += __shfl_xor_sync(0xffffffffu, tv, 1);
+                if (S.uh == 2) tv += __shfl_xor_sync(0xffffffffu, tv, 8);
+                dz[j] = tv;
+              }
+              const int col = col0 + i;
+              const bool cok = col < p.NC;          // NC % 4 == 0 on this path
+              float4 x = make_float4(0.f, 0.f, 0.f, 0.f), a = make_float4(1.f, 1.f, 1.f, 1.f), b = x, ctr = x;
+              if (cok) {
+                if (pf) x = xc[i >> 2];
+                else if (writer) x = ldg4(xrow + col);
+                if (S.pa) a = ldg4(S.pa + col);
+                if (S.pb) b = ldg4(S.pb + col);
+                if (do_s && E.center) ctr = ldg4(E.center + col);
+              }
+              const float xa[4] = {x.x, x.y, x.z, x.w}, aa[4] = {a.x, a.y, a.z, a.w}, ba[4] = {b.x, b.y, b.z, b.w},
+                          ca[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+              float du[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float tv = (writer && cok) ? dz[j] : 0.f;
+                if (S.relu && !(fmaf(aa[j], xa[j], ba[j]) > 0.f)) tv = 0.f;
+                du[j] = tv;
+              }
+              if (do_s) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float s1 = warp_sum(du[j]);
+                  float s2 = warp_sum(du[j] * (xa[j] - ca[j]));
+                  if (lane == i + j) { atomicAdd(&st_[(2 * e) * p.BN + cc + i + j], s1); atomicAdd(&st_[(2 * e + 1) * p.BN + cc + i + j], s2); }
+                }
+              }
+              if (writer && cok) {
+                float* q = E.mode == 0 ? const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff + col : E.du + ms * p.NC + col;
+                float4 g = E.mode == 0 ? make_float4(aa[0] * du[0], aa[1] * du[1], aa[2] * du[2], aa[3] * du[3])
+                                       : make_float4(du[0], du[1], du[2], du[3]);
+                if (atom) { atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w); }
+                else {
+                  if (E.accumulate) {
+                    const float4 o = pf ? oc[i >> 2] : *reinterpret_cast<float4*>(q);
+                    g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+                  }
+                  *reinterpret_cast<float4*>(q) = g;
+                }
+              }
+            }
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&acc_empty[ab]);
+        if (any_s) {
+          bar_epilogue();
+          for (int e = 0; e < p.nepi; ++e) {
+            const hdn_dgrad_epi& E = p.epi[e];
+            if (E.mode == 2 || E.s1 == nullptr) continue;
+            for (int c = etid; c < p.BN; c += 128) {
+              const int col = n_tile * p.BN + c;
+              if (col < p.NC) {
+                const float s1 = st_[(2 * e) * p.BN + c], s2 = st_[(2 * e + 1) * p.BN + c];
+                if (s1 != 0.f) atomicAdd(E.s1 + col, (double)s1);
+                if (s2 != 0.f) atomicAdd(E.s2 + col, (double)s2);
+              }
+            }
+          }
         }
       }
-      tc::umma_commit(acc_full);
     }
   }
 
@@ -494,12 +690,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------- weight packing
-// out[n_tile][kb][tap][chunk j][n][8]  (bf16)  =  B[n = column][k = kb*64 + j*8 + e]
+// out[n_tile][kb][tap][chunk j < KC/8][n][8]  (bf16)  =  B[n = column][k = kb*KC + j*8 + e]
 //   role 0 (fprop): B[n][k] = w[tap][k][n]                       K = Cin,  NC = Cout
 //   role 1 (dgrad): B[n][k] = w[flip(tap)][n][k]                 K = Cout, NC = Cin
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int Cin, int Cout, int kd, int kh, int kw, int BN, int KB,
-                                                           int n_tiles, int role, long long total16) {
+                                                           int KC, int role, long long total16) {
   // one thread per 16-byte output unit (n, chunk j): 8 consecutive k.  role 0 reads w[tap][k][col] (threads
   // adjacent in n -> coalesced over col); role 1 reads w[tap'][col][k..k+8) (two float4 per thread).
   const int T = kd * kh * kw;
@@ -507,11 +703,12 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total16; idx += (long long)gridDim.x * 256) {
     long long t = idx;
     const int n = (int)(t % BN); t /= BN;
-    const int j = (int)(t % 8); t /= 8;
+    const int nj = KC / 8;
+    const int j = (int)(t % nj); t /= nj;
     const int tap = (int)(t % T); t /= T;
     const int kb = (int)(t % KB); t /= KB;
     const int nt = (int)t;
-    const int k0 = kb * 64 + j * 8, col = nt * BN + n;
+    const int k0 = kb * KC + j * 8, col = nt * BN + n;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
@@ -582,7 +779,8 @@ __global__ void __launch_bounds__(256) zero_window_kernel(hdn_tensor t, long lon
 }
 
 struct TcPlan {
-  int BN, n_tiles, KB, nsb, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
+  int BN, n_tiles, KB, CK, nsb, nraw, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
+  int PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], raw_bytes, tab_src[2], tab_vq[2], tab_ints;
   long long ws_elems;
   size_t smem;
 };
@@ -648,12 +846,15 @@ TcGeom tc_geom(const hdn_conv* c, int mode) {
   return g;
 }
 
-TcPlan tc_plan(const hdn_conv* c, const TcGeom& g) {
+TcPlan tc_plan(const hdn_conv* c, const TcGeom& g, int mode) {
   TcPlan pl;
+  memset(&pl, 0, sizeof(pl));
   pl.n_tiles = (g.NC + 255) / 256;
   int bn = (g.NC + pl.n_tiles - 1) / pl.n_tiles;
   pl.BN = (bn + 15) / 16 * 16;
-  pl.KB = (g.K + 63) / 64;
+  const int nsrc = mode == 0 ? c->nsrc : 1;               // dgrad: the A operand is dY alone
+  pl.CK = (nsrc == 2) ? 32 : 64;                          // channels per stage (two raw patches must fit a stage)
+  pl.KB = (g.K + pl.CK - 1) / pl.CK;
   pl.flat = g.flat;
   pl.PH = 16 + g.kh - 1;
   pl.PW = 8 + g.kw - 1;
@@ -661,20 +862,45 @@ TcPlan tc_plan(const hdn_conv* c, const TcGeom& g) {
   pl.Ppad = pl.P | 1;
   pl.tiles_h = (c->H + 15) / 16;
   pl.tiles_w = (c->W + 7) / 8;
-  const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * 128;
-  int nsb = (int)((96 * 1024) / b_bytes);
+  int off = 0, toff = 0;
+  for (int s = 0; s < 2; ++s) {
+    pl.PHs[s] = pl.PH; pl.PWs[s] = pl.PW;
+    if (s < nsrc && mode == 0 && !g.s2d) {
+      if (c->src[s].uh == 2) pl.PHs[s] = pl.PH / 2 + 1;
+      if (c->src[s].uw == 2) pl.PWs[s] = pl.PW / 2 + 1;
+    }
+    pl.Ps[s] = s < nsrc ? pl.PHs[s] * pl.PWs[s] : 0;
+    pl.raw_off[s] = off;
+    off += pl.Ps[s] * pl.CK * 4;
+    pl.tab_src[s] = toff; toff += pl.Ps[s];
+    pl.tab_vq[s] = toff; toff += s < nsrc ? pl.P : 0;
+  }
+  for (int s = 0; s < 2; ++s) { pl.ab_off[s] = off; off += s < nsrc ? 2 * pl.CK * 4 : 0; }
+  pl.raw_bytes = (off + 127) / 128 * 128;
+  pl.tab_ints = toff;
+  const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * pl.CK * 2;
+  int nsb = (int)((48 * 1024) / b_bytes);
   pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
   int cols = 32;
-  while (cols < pl.BN) cols *= 2;
+  while (cols < 2 * pl.BN) cols *= 2;                      // two accumulator buffers
   pl.tmem_cols = cols;
-  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * 64;
-  pl.smem = NSA * a_bytes + pl.nsb * b_bytes + 2ull * pl.P * 4 + 4ull * pl.BN * 4 + 16 + (2 * NSA + 2 * NSB_MAX + 1) * 8 + 16;
+  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * pl.CK;
+  const size_t fixed = NSA * a_bytes + pl.nsb * b_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 +
+                       (2 * NSA + 2 * NSB_MAX + 4) * 8 + 16;
+  if (g.s2d) pl.nraw = 0;
+  else {
+    long long room = (long long)(226 * 1024) - (long long)fixed;
+    int nraw = (int)(room / pl.raw_bytes);
+    pl.nraw = nraw > NRAW_MAX ? NRAW_MAX : nraw;
+  }
+  pl.smem = fixed + (size_t)pl.nraw * pl.raw_bytes;
   return pl;
 }
 
 int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_t st) {
   const TcGeom g = tc_geom(c, mode);
-  const TcPlan pl = tc_plan(c, g);
+  const TcPlan pl = tc_plan(c, g, mode);
+  HDN_CHECK_ARG(g.s2d || pl.nraw >= 2, "conv tc: shared memory cannot hold two raw stages (BN=%d)", pl.BN);
   HDN_CHECK_ARG(c->ws != nullptr && c->ws_bytes >= pl.ws_elems * 2, "conv tc: workspace too small (%lld < %lld bytes)",
                 (long long)c->ws_bytes, (long long)pl.ws_elems * 2);
   static bool attr_set = false;
@@ -690,7 +916,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     if (g.s2d || g.scatter)
       pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, mode, total);
     else
-      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.n_tiles, mode, total);
+      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, total);
     HDN_CHECK_LAUNCH("pack_weights");
   }
   TcParams p;
@@ -700,8 +926,13 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.pd_lo = g.pd_lo; p.ph_lo = g.ph_lo; p.pw_lo = g.pw_lo;
   p.s2d = g.s2d; p.s2d_quads = g.quads; p.scatter = g.scatter;
   p.K = g.K; p.NC = g.NC;
-  p.BN = pl.BN; p.KB = pl.KB; p.nsb = pl.nsb; p.tmem_cols = pl.tmem_cols;
+  p.BN = pl.BN; p.KB = pl.KB; p.CK = pl.CK; p.nsb = pl.nsb; p.nraw = pl.nraw; p.tmem_cols = pl.tmem_cols;
   p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad;
+  for (int s = 0; s < 2; ++s) {
+    p.PHs[s] = pl.PHs[s]; p.PWs[s] = pl.PWs[s]; p.Ps[s] = pl.Ps[s]; p.raw_off[s] = pl.raw_off[s]; p.ab_off[s] = pl.ab_off[s];
+    p.tab_src[s] = pl.tab_src[s]; p.tab_vq[s] = pl.tab_vq[s];
+  }
+  p.raw_bytes = pl.raw_bytes; p.tab_ints = pl.tab_ints;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h;
   p.M = (long long)c->N * c->D * c->H * c->W;
   p.wpack = wp;
@@ -744,8 +975,15 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     }
   }
   const long long tiles = pl.flat ? (p.M + 127) / 128 : (long long)c->N * c->D * pl.tiles_h * pl.tiles_w;
-  HDN_CHECK_ARG(tiles < (1ll << 31), "conv tc: too many tiles");
-  dim3 grid((unsigned)tiles, (unsigned)pl.n_tiles);
+  p.tiles = tiles;
+  p.total_work = tiles * pl.n_tiles;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const unsigned grid = (unsigned)(p.total_work < num_sms ? p.total_work : num_sms);   // persistent: one CTA per SM
   conv_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p);
   HDN_CHECK_LAUNCH(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
   return HDN_OK;
@@ -770,7 +1008,7 @@ int hdn_tc_supported(const hdn_conv* c, int pass) {
 
 long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
   if (!hdn_tc_supported(c, pass) || pass == 2) return 0;
-  return tc_plan(c, tc_geom(c, pass)).ws_elems * 2;
+  return tc_plan(c, tc_geom(c, pass), pass).ws_elems * 2;
 }
 
 int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st) { return tc_launch(c, nullptr, 0, st); }

@@ -24,15 +24,17 @@ __global__ void __launch_bounds__(ET) maxpool_fwd(const hdn_pool p, const int64_
     hdn_decode(m, p.D, p.H, p.W, n, od, oh, ow);
     const int d_lo = p.pool_d ? 2 * od - 1 : od, d_hi = p.pool_d ? 2 * od + 1 : od;
     float best = -INFINITY;
+    int arg = 0, idx = 0;
     for (int d = d_lo; d <= d_hi; ++d)
       for (int h = 2 * oh - 1; h <= 2 * oh + 1; ++h)
-        for (int w = 2 * ow - 1; w <= 2 * ow + 1; ++w) {
+        for (int w = 2 * ow - 1; w <= 2 * ow + 1; ++w, ++idx) {
           float v = 0.f;   // zero padding (ZeroPadding + VALID max-pool)
           if (d >= 0 && d < s.D && h >= 0 && h < s.H && w >= 0 && w < s.W)
             v = hdn_prologue(s, __ldg(s.t.p + hdn_src_off(s, n, d, h, w) + c), c);
-          best = fmaxf(best, v);
+          if (v > best) { best = v; arg = idx; }     // first maximum in scan order (d, h, w)
         }
     ((float*)p.y.p)[m * p.y.ldc + p.y.coff + c] = best;
+    if (p.argidx) p.argidx[i] = (unsigned char)arg;
   }
 }
 
@@ -100,6 +102,42 @@ __global__ void __launch_bounds__(ET) maxpool_bwd(const hdn_pool p, const hdn_dg
       }
     }
     float du = (s.relu && !(u > 0.f)) ? 0.f : dz;
+    if (e.s1 && du != 0.f) { atomicAdd(&bins[c], du); atomicAdd(&bins[p.C + c], du * (x - (e.center ? __ldg(e.center + c) : 0.f))); }
+    epi_store(e, m, c, p.C, a, du);
+  }
+  if (e.s1) bins_flush(bins, p.C, e.s1, e.s2);
+}
+
+// backward with the arg-max taps saved by the forward pass: an input element receives dY of every window
+// whose saved tap points at it (<= 2 windows per pooled axis)
+__global__ void __launch_bounds__(ET) maxpool_bwd_idx(const hdn_pool p, const hdn_dgrad_epi e, const int64_t total) {
+  extern __shared__ float bins[];
+  const hdn_src& s = p.src;
+  if (e.s1) bins_init(bins, p.C);
+  for (int64_t i = blockIdx.x * (int64_t)ET + threadIdx.x; i < total; i += (int64_t)gridDim.x * ET) {
+    int c = (int)(i % p.C);
+    int64_t m = i / p.C;
+    int n, id, ih, iw;
+    hdn_decode(m, s.D, s.H, s.W, n, id, ih, iw);
+    float dz = 0.f;
+    const int odl = p.pool_d ? id / 2 : id, odh = p.pool_d ? (id + 1) / 2 : id;
+    for (int od = odl; od <= odh; ++od) {
+      if (od >= p.D) continue;
+      const int td = p.pool_d ? id - (2 * od - 1) : 0;
+      for (int oh = ih / 2; oh <= (ih + 1) / 2; ++oh) {
+        if (oh >= p.H) continue;
+        const int th = ih - (2 * oh - 1);
+        for (int ow = iw / 2; ow <= (iw + 1) / 2; ++ow) {
+          if (ow >= p.W) continue;
+          const int tw = iw - (2 * ow - 1);
+          const int64_t mo = (((int64_t)n * p.D + od) * p.H + oh) * p.W + ow;
+          if (p.argidx[mo * p.C + c] == (unsigned char)((td * 3 + th) * 3 + tw)) dz += __ldg(p.y.p + mo * p.y.ldc + p.y.coff + c);
+        }
+      }
+    }
+    const float x = __ldg(s.t.p + m * s.t.ldc + s.t.coff + c);
+    const float a = s.pa ? __ldg(s.pa + c) : 1.f, b = s.pb ? __ldg(s.pb + c) : 0.f;
+    float du = (s.relu && !(fmaf(a, x, b) > 0.f)) ? 0.f : dz;
     if (e.s1 && du != 0.f) { atomicAdd(&bins[c], du); atomicAdd(&bins[p.C + c], du * (x - (e.center ? __ldg(e.center + c) : 0.f))); }
     epi_store(e, m, c, p.C, a, du);
   }
@@ -391,7 +429,8 @@ extern "C" int hdn_pool_bwd(const hdn_pool* p, const hdn_dgrad_epi* e, void* str
   const int64_t total = (int64_t)p->N * p->src.D * p->src.H * p->src.W * p->C;
   HDN_CHECK_ARG(p->C <= 4096, "pool_bwd: C > 4096 unsupported");
   const size_t sm = e->s1 ? 2 * (size_t)p->C * sizeof(float) : 0;
-  if (p->kind == 0) maxpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
+  if (p->kind == 0 && p->argidx) maxpool_bwd_idx<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
+  else if (p->kind == 0) maxpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
   else avgpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
   HDN_CHECK_LAUNCH("pool_bwd");
   return HDN_OK;

@@ -236,6 +236,7 @@ class CudaBackend(object):
             c.pool_d = d.pool_d
             c.src = self._src(d.src)
             c.y = self._tensor(d.out, grad=y_grad)
+            c.argidx = _ptr(getattr(d, "argidx", None))
             d.__dict__[key] = c
         return c
 
@@ -581,6 +582,9 @@ class PoolOp(object):
     def compile(self):
         o = self.out
         self.desc = PoolDesc(self.kind, o, self.src, self.pool_d)
+        if self.kind == 0 and self.net.training and self.net.device.type == "cuda":
+            # arg-max taps saved by the forward pass for the backward pass (1 byte per pooled element)
+            self.desc.argidx = torch.zeros(o.M * o.C, dtype=torch.uint8, device=self.net.device)
         self.stat = None
         if o.buf.need_stats[o.coff:o.coff + o.C].any():
             self.stat = (o.buf.stats[0][o.coff:o.coff + o.C], o.buf.stats[1][o.coff:o.coff + o.C])

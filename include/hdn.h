@@ -112,6 +112,8 @@ typedef struct {
   int pool_d;             /* kind 0: 1 => also pool depth (3-D), 0 => 2-D */
   hdn_src src;
   hdn_tensor y;           /* output (fwd) / dY (bwd) */
+  unsigned char* argidx;  /* kind 0, optional: dense [N*D*H*W][C] arg-max tap (scan order d,h,w) written by
+                             hdn_pool_fwd and read by hdn_pool_bwd; NULL => backward recomputes the windows */
 } hdn_pool;
 int hdn_pool_fwd(const hdn_pool* p, void* stream);
 int hdn_pool_bwd(const hdn_pool* p, const hdn_dgrad_epi* epi, void* stream);

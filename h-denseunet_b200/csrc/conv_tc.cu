@@ -8,7 +8,7 @@
 // Persistent kernel, one CTA per SM, each CTA loops over 128 x BN output tiles (128 GEMM rows =
 // 16 x 8 output pixels of one (n, d) slice, or 128 consecutive positions for 1x1x1).
 //
-//   warps 0-3  producers.  Stage = one channel block (64, or 32 with two sources) of the fp32 input
+//   warps 0-7  producers.  Stage = one channel block (64, or 32 with two sources) of the fp32 input
 //              PATCH (tile + halo) of one depth slab.  The raw fp32 patch is fetched with cp.async
 //              (16-byte copies, several stages in flight, no registers held), then transformed once:
 //              max(a*x+b, 0) (+ second source, nearest-neighbour up-sampling in the index), bf16, stored
@@ -16,22 +16,26 @@
 //              Every filter tap is the SAME shared-memory patch read through a descriptor whose start
 //              address is shifted by (th*PW + tw)*16 bytes and whose 8-row-group stride is PW*16 bytes:
 //              no im2col gather, each input element is loaded once per tile instead of once per tap.
-//   warp 4     weight loader: one elected thread streams pre-packed bf16 weight blocks (already in
+//   warp 8     weight loader: one elected thread streams pre-packed bf16 weight blocks (already in
 //              core-matrix order) with cp.async.bulk (TMA engine) on mbarriers.
-//   warp 5     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
+//   warp 9     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //              TMEM accumulator buffers and releases stages with tcgen05.commit.
-//   warps 6-9  epilogue: tcgen05.ld the finished accumulator while the next tile's MMAs run.
+//   warps 10-13 epilogue: tcgen05.ld the finished accumulator while the next tile's MMAs run.
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
+constexpr int NPROD = 256;        // producer threads
 constexpr int NSA = 2;        // bf16 A-operand stages
-constexpr int NSB_MAX = 4;    // weight-block ring depth upper bound
+constexpr int NSB_MAX = 16;   // weight-block ring depth upper bound
 constexpr int NRAW_MAX = 4;   // raw fp32 patch ring depth upper bound
 constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs < NRAW_MAX tiles ahead of the transform)
-constexpr int UB = 4;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
+constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
+constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
+constexpr int RB = 16;        // dgrad epilogue: rows fetched ahead per lane
+constexpr int TU = 3;         // transform: pixel groups looked up / fetched ahead per warp
 
 struct TcParams {
   int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
@@ -135,7 +139,7 @@ __device__ __forceinline__ void cp_async_wait(int n) {     // n groups may remai
     default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
   }
 }
-__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
 
 // Regroup the two channel quads a lane holds ([4*l8, +4) and [32 + 4*l8, +4)) with its neighbour lane into
@@ -154,6 +158,31 @@ __device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q,
   if (qok) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
 }
 
+// Column sums over the 32 rows (lanes) of a warp for 16 columns held one row per lane, by recursive halving:
+// 16 shuffles instead of 16 x 5.  Every lane returns the total of column (lane >> 1).  v is clobbered.
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = (lane & 16) ? v[i] : v[i + 8], keep = (lane & 16) ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = (lane & 8) ? v[i] : v[i + 4], keep = (lane & 8) ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = (lane & 4) ? v[i] : v[i + 2], keep = (lane & 4) ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,7 +193,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint8_t* sRaw = sB + p.nsb * B_BYTES;
   int* tabs = reinterpret_cast<int*>(sRaw + (size_t)p.nraw * p.raw_bytes);
   float* sstat = reinterpret_cast<float*>(tabs + NTAB * p.tab_ints);        // [2 buffers][4][BN]
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 15) & ~uintptr_t(15));
+  uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 15) & ~uintptr_t(15));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * EPI_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + NSA;
   uint64_t* b_full = a_empty + NSA;
@@ -174,12 +204,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < NSA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NSA; ++i) { tc::mbar_init(&a_full[i], NPROD); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB_MAX; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
   }
-  if (warp == 5) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == 9) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -188,9 +218,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int taps_hw = p.kh * p.kw;
   const int T = p.kd * taps_hw;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =================================================================== A producers
-    const int ptid = tid;                                 // 0..127
+    const int ptid = tid;                                 // 0..255
     const int l8 = lane & 7, pg = lane >> 3;
     int built_seq = -1;
 
@@ -203,7 +233,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const hdn_src& S = p.src[s];
         const int vh0 = t.h0 - p.ph_lo, vw0 = t.w0 - p.pw_lo;
         const int sh0 = (S.uh == 2) ? (vh0 >> 1) : vh0, sw0 = (S.uw == 2) ? (vw0 >> 1) : vw0;
-        for (int i = ptid; i < p.Ps[s]; i += 128) {
+        for (int i = ptid; i < p.Ps[s]; i += NPROD) {
           int off = -1;
           if (p.flat) {
             if (t.m0 + i < p.M) off = i * S.t.ldc;
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           tab[p.tab_src[s] + i] = off;
         }
-        for (int q = ptid; q < p.P; q += 128) {
+        for (int q = ptid; q < p.P; q += NPROD) {
           int sq = -1;
           if (p.flat) {
             if (t.m0 + q < p.M) sq = q;
@@ -222,7 +252,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const int vh = vh0 + q / p.PW, vw = vw0 + q % p.PW;
             if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
               const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
-              sq = (sh - sh0) * p.PWs[s] + (sw - sw0);
+              sq = (sh - sh0) * p.PWs[s] + (sw - sw0);        // a valid virtual pixel always maps to a valid source pixel
             }
           }
           tab[p.tab_vq[s] + q] = sq;
@@ -247,7 +277,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // ---- asynchronous path: raw fp32 patch -> shared memory with cp.async, several stages ahead
       StageIt is;
       it_init(p, is);
-      const int NQ = p.CK >> 2;                            // 16-byte quads per pixel in a raw stage
+      const int NQ = p.CK >> 2;                            // 16-byte quads per pixel in a raw stage (16 or 8)
+      const int NQs = (p.CK == 64) ? 4 : 3;
       auto issue = [&](const StageIt& it, int slot) {
         if (it.seq != built_seq) { build_tables(it); built_seq = it.seq; }
         const int* tab = tabs + (it.seq % NTAB) * p.tab_ints;
@@ -259,8 +290,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int* spix = tab + p.tab_src[s];
           uint8_t* rs = raw + p.raw_off[s];
           const int n16 = p.Ps[s] * NQ;
-          for (int i = ptid; i < n16; i += 128) {
-            const int sq = i / NQ, part = i - sq * NQ;
+          for (int i = ptid; i < n16; i += NPROD) {
+            const int sq = i >> NQs, part = i & (NQ - 1);
             const int off = spix[sq], c = c0 + part * 4;
             if (off >= 0 && c < p.K) cp_async16(rs + (size_t)i * 16, base + off + c);
           }
@@ -301,25 +332,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (p.src[s].pb) { if (okA) b0[s] = *reinterpret_cast<const float4*>(ab + p.CK + cA); if (okB) b1[s] = *reinterpret_cast<const float4*>(ab + p.CK + cB); }
             }
           }
-          for (int q0 = warp * 4; q0 < p.P; q0 += 16) {
-            const int q = q0 + pg;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (q < p.P) {
+          // TU pixel groups per warp are looked up and fetched before any is processed (latency overlap)
+          const float* rawf0 = reinterpret_cast<const float*>(raw + p.raw_off[0]);
+          const float* rawf1 = reinterpret_cast<const float*>(raw + p.raw_off[1]);
+          const int* vq0 = tab + p.tab_vq[0];
+          const int* vq1 = tab + p.tab_vq[1];
+          const int relu0 = p.src[0].relu, relu1 = p.nsrc > 1 ? p.src[1].relu : 0;
+          for (int q0 = warp * 4; q0 < p.P; q0 += 32 * TU) {
+            int sq0[TU], sq1[TU];
 #pragma unroll
-              for (int s = 0; s < 2; ++s) {
-                if (s < p.nsrc) {
-                  const int sq = tab[p.tab_vq[s] + q];
-                  const int off = sq >= 0 ? tab[p.tab_src[s] + sq] : -1;      // zero padding is applied AFTER BN/Scale/ReLU
-                  if (off >= 0) {
-                    const float* row = reinterpret_cast<const float*>(raw + p.raw_off[s]) + (size_t)sq * p.CK;
-                    const int relu = p.src[s].relu;
-                    if (okA) { float4 t = prologue4(*reinterpret_cast<const float4*>(row + cA), a0[s], b0[s], relu); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
-                    if (okB) { float4 t = prologue4(*reinterpret_cast<const float4*>(row + cB), a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
-                  }
-                }
+            for (int u = 0; u < TU; ++u) {
+              const int q = q0 + u * 32 + pg;
+              sq0[u] = sq1[u] = -1;
+              if (q < p.P) { sq0[u] = vq0[q]; if (p.nsrc > 1) sq1[u] = vq1[q]; }
+            }
+            float4 x0a[TU], x0b[TU], x1a[TU], x1b[TU];
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+              x0a[u] = x0b[u] = x1a[u] = x1b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (sq0[u] >= 0) {
+                const float* row = rawf0 + sq0[u] * p.CK;
+                if (okA) x0a[u] = *reinterpret_cast<const float4*>(row + cA);
+                if (okB) x0b[u] = *reinterpret_cast<const float4*>(row + cB);
+              }
+              if (sq1[u] >= 0) {
+                const float* row = rawf1 + sq1[u] * p.CK;
+                if (okA) x1a[u] = *reinterpret_cast<const float4*>(row + cA);
+                if (okB) x1b[u] = *reinterpret_cast<const float4*>(row + cB);
               }
             }
-            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, v0, v1, lane);
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+              if (q0 + u * 32 >= p.P) break;                 // warp-uniform
+              const int q = q0 + u * 32 + pg;
+              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+              if (sq0[u] >= 0) {                             // zero padding is applied AFTER BN/Scale/ReLU
+                if (okA) v0 = prologue4(x0a[u], a0[0], b0[0], relu0);
+                if (okB) v1 = prologue4(x0b[u], a1[0], b1[0], relu0);
+              }
+              if (sq1[u] >= 0) {
+                if (okA) { float4 t = prologue4(x1a[u], a0[1], b0[1], relu1); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
+                if (okB) { float4 t = prologue4(x1b[u], a1[1], b1[1], relu1); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
+              }
+              store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, v0, v1, lane);
+            }
           }
         }
         tc::fence_proxy_async_smem();
@@ -342,11 +398,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                             S.t.coff + s2d_add;
         tc::mbar_wait(&a_empty[sa], pha ^ 1);
         uint8_t* dst = sA + sa * A_BYTES;
-        for (int q0 = warp * 4; q0 < p.P; q0 += 16 * UB) {
+        for (int q0 = warp * 4; q0 < p.P; q0 += 32 * UB) {
           float4 r0[UB];
 #pragma unroll
           for (int u = 0; u < UB; ++u) {
-            const int q = q0 + u * 16 + pg;
+            const int q = q0 + u * 32 + pg;
             r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (q < p.P && okA) {
               const int sq = tab[p.tab_vq[0] + q];
@@ -356,8 +412,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
 #pragma unroll
           for (int u = 0; u < UB; ++u) {
-            if (q0 + u * 16 >= p.P) break;                  // warp-uniform
-            const int q = q0 + u * 16 + pg;
+            if (q0 + u * 32 >= p.P) break;                  // warp-uniform
+            const int q = q0 + u * 32 + pg;
             store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, r0[u], make_float4(0.f, 0.f, 0.f, 0.f), lane);
           }
         }
@@ -367,7 +423,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         it_next(p, tr);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // =================================================================== weight loader (TMA engine)
     if (lane == 0) {
       StageIt it;
@@ -379,7 +435,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const __nv_bfloat16* wp = p.wpack + (size_t)it.t.n_tile * p.KB * T * blk;
         for (int t2 = 0; t2 < taps_hw; ++t2) {
           const int tap = it.dz * taps_hw + t2;
-          tc::mbar_wait(&b_empty[sb], phb ^ 1);
+          tc::mbar_wait_sleep(&b_empty[sb], phb ^ 1);
           tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
           tc::bulk_g2s(sB + sb * B_BYTES, wp + ((size_t)it.kb * T + tap) * blk, B_BYTES, &b_full[sb]);
           if (++sb == p.nsb) { sb = 0; phb ^= 1; }
@@ -387,7 +443,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         it_next(p, it);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 0, 0);
@@ -436,8 +492,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else {
-    // =================================================================== epilogue (warps 6-9)
-    const int etid = tid - 192;                             // 0..127
+    // =================================================================== epilogue (warps 10-13)
+    const int etid = tid - 320;                             // 0..127
+    uint8_t* escr = sEpi + (size_t)(warp - 10) * EPI_BYTES;  // this warp's transpose tile + row-offset tables
+    float* tT = reinterpret_cast<float*>(escr);             // [32][33]
+    long long* ro0 = reinterpret_cast<long long*>(escr + 32 * 33 * 4);   // [32]  output row offsets (fprop)
+    long long* rox = ro0;                                    // [2][32] stored-value row offsets (dgrad)
+    long long* rod = ro0 + 64;                               // [2][32] gradient row offsets (dgrad)
     const int qtr = warp & 3;                               // TMEM lane quarter this warp may read
     const int row = qtr * 32 + lane;
     const int hr = row >> 3, wr = row & 7;
@@ -467,48 +528,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int i = etid; i < 4 * p.BN; i += 128) st_[i] = 0.f;
         bar_epilogue();
       }
-      tc::mbar_wait(&acc_full[ab], (uint32_t)(seq >> 1) & 1u);
+      tc::mbar_wait_sleep(&acc_full[ab], (uint32_t)(seq >> 1) & 1u);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * p.BN);
 
       if (p.mode == 0) {
+        // Transposed epilogue: the warp's 32 x 32 accumulator block goes through shared memory so that lane = output
+        // channel and the 32 lanes write 128 contiguous bytes of one output pixel; the per-channel batch statistics
+        // become plain per-lane running sums (no shuffles).
         const bool do_stats = p.stat_sum != nullptr;
-        const bool vec = (p.NC % 4 == 0) && (p.y.ldc % 4 == 0) && (p.y.coff % 4 == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0);
-        float* yrow = const_cast<float*>(p.y.p) + m * p.y.ldc + p.y.coff;
-        for (int cc = 0; cc < p.BN; cc += 16) {
-          tc::tmem_ld16(taddr + cc, v);
-          const int col0 = n_tile * p.BN + cc;
+        const bool has_bias = p.bias != nullptr, drop = p.drop_keep < 1.0f;
+        float* ybase = const_cast<float*>(p.y.p) + p.y.coff;
+        ro0[lane] = m * (long long)p.y.ldc;
+        rod[lane] = m;                                      // linear position (dropout hash index)
+        const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
+        __syncwarp();
+        for (int cb = 0; cb < p.BN; cb += 32) {
+          const int ncols = min(32, p.BN - cb);
+          float v2[16];
+          tc::tmem_ld16(taddr + cb, v);
+          if (ncols > 16) tc::tmem_ld16(taddr + cb + 16, v2);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int col = col0 + i;
-            float tv = v[i];
-            if (col < p.NC) {
-              if (p.bias) tv += __ldg(p.bias + col);
-              if (p.drop_keep < 1.0f) tv *= hdn_drop_scale(p.drop_seed, (uint64_t)m * p.NC + col, p.drop_keep);
-            }
-            v[i] = tv;
+          for (int i = 0; i < 16; ++i) tT[lane * 33 + i] = v[i];
+          if (ncols > 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tT[lane * 33 + 16 + i] = v2[i];
           }
-          if (rvalid) {
-            if (vec) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                if (col0 + i < p.NC) *reinterpret_cast<float4*>(yrow + col0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (col0 + i < p.NC) yrow[col0 + i] = v[i];
+          __syncwarp();
+          const int col = n_tile * p.BN + cb + lane;
+          const bool cok = lane < ncols && col < p.NC;
+          const float bias = (has_bias && cok) ? __ldg(p.bias + col) : 0.f;
+          float ssum = 0.f, ssq = 0.f;
+          if (cok) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              if (!((vmask >> rr) & 1u)) continue;             // warp-uniform
+              float tv = tT[rr * 33 + lane] + bias;
+              const long long ro = ro0[rr];
+              if (drop) tv *= hdn_drop_scale(p.drop_seed, (uint64_t)rod[rr] * p.NC + col, p.drop_keep);
+              ybase[ro + col] = tv;
+              ssum += tv; ssq += tv * tv;
             }
+            if (do_stats) { atomicAdd(&st_[cb + lane], ssum); atomicAdd(&st_[p.BN + cb + lane], ssq); }
           }
-          if (do_stats) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float s = rvalid ? v[i] : 0.f;
-              float q2 = s * s;
-              s = warp_sum(s); q2 = warp_sum(q2);
-              if (lane == i) { atomicAdd(&st_[cc + i], s); atomicAdd(&st_[p.BN + cc + i], q2); }
-            }
-          }
+          __syncwarp();
         }
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[ab]);                   // accumulator buffer may be overwritten
@@ -546,119 +609,92 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[ab]);
       } else {
-        // dgrad: v = dz at a (virtual-resolution) input position; per source: reduce the up-sampling
-        // sub-positions, ReLU mask from the stored value, S1/S2 sums, then dx (+)= a*du or du (+)= du.
-        // The stored value x and (when accumulating) the old gradient of the NEXT column chunk are requested
-        // before the current chunk is processed: the epilogue is a stream of dependent global loads otherwise.
-        const bool pf = p.nepi == 1 && p.epi[0].mode != 2;
-        float4 xn[4], on[4];
-        long long ms0 = m;
-        bool writer0 = rvalid;
-        const float* xrow0 = nullptr;
-        float* orow0 = nullptr;
-        bool rmw0 = false;
-        if (pf) {
-          const hdn_src& S = p.esrc[0];
-          const hdn_dgrad_epi& E = p.epi[0];
+        // dgrad, transposed like fprop: lane = input channel.  For each source and each writer row: dz (summed over the
+        // up-sampling sub-positions of the row), ReLU mask from the stored value, per-lane S1/S2 running sums, then
+        // dx (+)= a*du or du (+)= du as coalesced 128-byte row accesses.
+        unsigned wmask[2] = {0u, 0u};
+        for (int e = 0; e < p.nepi; ++e) {
+          if (p.epi[e].mode == 2) continue;
+          const hdn_src& S = p.esrc[e];
+          const hdn_dgrad_epi& E = p.epi[e];
+          long long ms = m;
+          bool writer = rvalid;
           if (!p.flat) {
             const int sd = (S.ud == 2) ? (t.d0 >> 1) : t.d0, sh = (S.uh == 2) ? (oh >> 1) : oh, sw = (S.uw == 2) ? (ow >> 1) : ow;
-            ms0 = (((long long)t.n_img * S.D + sd) * S.H + sh) * S.W + sw;
-            if (S.uw == 2 && (wr & 1)) writer0 = false;
-            if (S.uh == 2 && (hr & 1)) writer0 = false;
+            ms = (((long long)t.n_img * S.D + sd) * S.H + sh) * S.W + sw;
+            if (S.uw == 2 && (wr & 1)) writer = false;
+            if (S.uh == 2 && (hr & 1)) writer = false;
           }
-          xrow0 = S.t.p + ms0 * S.t.ldc + S.t.coff;
-          rmw0 = E.accumulate && S.ud != 2;
-          orow0 = E.mode == 0 ? const_cast<float*>(E.dx.p) + ms0 * E.dx.ldc + E.dx.coff : E.du + ms0 * p.NC;
+          rox[e * 32 + lane] = ms * (long long)S.t.ldc + S.t.coff;
+          rod[e * 32 + lane] = E.mode == 0 ? ms * (long long)E.dx.ldc + E.dx.coff : ms * (long long)p.NC;
+          wmask[e] = __ballot_sync(0xffffffffu, writer);
         }
-        auto prefetch = [&](int cc) {
-          const int col0 = n_tile * p.BN + cc;
+        const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
+        __syncwarp();
+        for (int cb = 0; cb < p.BN; cb += 32) {
+          const int ncols = min(32, p.BN - cb);
+          float v2[16];
+          tc::tmem_ld16(taddr + cb, v);
+          if (ncols > 16) tc::tmem_ld16(taddr + cb + 16, v2);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            xn[i] = on[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (writer0 && col0 + 4 * i < p.NC) {
-              xn[i] = ldg4(xrow0 + col0 + 4 * i);
-              if (rmw0) on[i] = *reinterpret_cast<const float4*>(orow0 + col0 + 4 * i);
-            }
-          }
-        };
-        if (pf) prefetch(0);
-        for (int cc = 0; cc < p.BN; cc += 16) {
-          float4 xc[4], oc[4];
-          if (pf) {
+          for (int i = 0; i < 16; ++i) tT[lane * 33 + i] = rvalid ? v[i] : 0.f;
+          if (ncols > 16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { xc[i] = xn[i]; oc[i] = on[i]; }
-            if (cc + 16 < p.BN) prefetch(cc + 16);
+            for (int i = 0; i < 16; ++i) tT[lane * 33 + 16 + i] = rvalid ? v2[i] : 0.f;
           }
-          tc::tmem_ld16(taddr + cc, v);
-          const int col0 = n_tile * p.BN + cc;
+          __syncwarp();
+          const int col = n_tile * p.BN + cb + lane;
+          const bool cok = lane < ncols && col < p.NC;
           for (int e = 0; e < p.nepi; ++e) {
             const hdn_dgrad_epi& E = p.epi[e];
             if (E.mode == 2) continue;
             const hdn_src& S = p.esrc[e];
-            long long ms = m;
-            bool writer = rvalid;
-            if (!p.flat) {
-              const int sd = (S.ud == 2) ? (t.d0 >> 1) : t.d0, sh = (S.uh == 2) ? (oh >> 1) : oh, sw = (S.uw == 2) ? (ow >> 1) : ow;
-              ms = (((long long)t.n_img * S.D + sd) * S.H + sh) * S.W + sw;
-              if (S.uw == 2 && (wr & 1)) writer = false;
-              if (S.uh == 2 && (hr & 1)) writer = false;
-            }
-            const bool atom = (S.ud == 2);
-            const float* xrow = S.t.p + ms * S.t.ldc + S.t.coff;
-            const bool do_s = E.s1 != nullptr;
+            if (cok) {
+              const float a = S.pa ? __ldg(S.pa + col) : 1.f, b = S.pb ? __ldg(S.pb + col) : 0.f;
+              const float ctr = (E.s1 && E.center) ? __ldg(E.center + col) : 0.f;
+              const bool up_w = S.uw == 2, up_h = S.uh == 2, atom = S.ud == 2, acc = E.accumulate != 0, relu = S.relu != 0;
+              const float* xb = S.t.p;
+              float* db = E.mode == 0 ? const_cast<float*>(E.dx.p) : E.du;
+              const float ga = E.mode == 0 ? a : 1.f;
+              const long long* rx = rox + e * 32;
+              const long long* rd = rod + e * 32;
+              const unsigned wm = wmask[e];
+              float s1 = 0.f, s2 = 0.f;
+              // rows in batches of RB: all stored values (and old gradients) of a batch are requested before any is used
+              for (int r0 = 0; r0 < 32; r0 += RB) {
+                if (!((wm >> r0) & ((1u << RB) - 1u))) continue;   // warp-uniform: no writer row in this batch
+                float xs[RB], qs[RB];
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float dz[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float tv = rvalid ? v[i + j] : 0.f;
-                if (S.uw == 2) tv += __shfl_xor_sync(0xffffffffu, tv, 1);
-                if (S.uh == 2) tv += __shfl_xor_sync(0xffffffffu, tv, 8);
-                dz[j] = tv;
-              }
-              const int col = col0 + i;
-              const bool cok = col < p.NC;          // NC % 4 == 0 on this path
-              float4 x = make_float4(0.f, 0.f, 0.f, 0.f), a = make_float4(1.f, 1.f, 1.f, 1.f), b = x, ctr = x;
-              if (cok) {
-                if (pf) x = xc[i >> 2];
-                else if (writer) x = ldg4(xrow + col);
-                if (S.pa) a = ldg4(S.pa + col);
-                if (S.pb) b = ldg4(S.pb + col);
-                if (do_s && E.center) ctr = ldg4(E.center + col);
-              }
-              const float xa[4] = {x.x, x.y, x.z, x.w}, aa[4] = {a.x, a.y, a.z, a.w}, ba[4] = {b.x, b.y, b.z, b.w},
-                          ca[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
-              float du[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float tv = (writer && cok) ? dz[j] : 0.f;
-                if (S.relu && !(fmaf(aa[j], xa[j], ba[j]) > 0.f)) tv = 0.f;
-                du[j] = tv;
-              }
-              if (do_s) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float s1 = warp_sum(du[j]);
-                  float s2 = warp_sum(du[j] * (xa[j] - ca[j]));
-                  if (lane == i + j) { atomicAdd(&st_[(2 * e) * p.BN + cc + i + j], s1); atomicAdd(&st_[(2 * e + 1) * p.BN + cc + i + j], s2); }
-                }
-              }
-              if (writer && cok) {
-                float* q = E.mode == 0 ? const_cast<float*>(E.dx.p) + ms * E.dx.ldc + E.dx.coff + col : E.du + ms * p.NC + col;
-                float4 g = E.mode == 0 ? make_float4(aa[0] * du[0], aa[1] * du[1], aa[2] * du[2], aa[3] * du[3])
-                                       : make_float4(du[0], du[1], du[2], du[3]);
-                if (atom) { atomicAdd(q, g.x); atomicAdd(q + 1, g.y); atomicAdd(q + 2, g.z); atomicAdd(q + 3, g.w); }
-                else {
-                  if (E.accumulate) {
-                    const float4 o = pf ? oc[i >> 2] : *reinterpret_cast<float4*>(q);
-                    g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w;
+                for (int k = 0; k < RB; ++k) {
+                  xs[k] = 0.f; qs[k] = 0.f;
+                  if ((wm >> (r0 + k)) & 1u) {
+                    xs[k] = __ldg(xb + rx[r0 + k] + col);
+                    if (acc && !atom) qs[k] = __ldcg(db + rd[r0 + k] + col);
                   }
-                  *reinterpret_cast<float4*>(q) = g;
+                }
+#pragma unroll
+                for (int k = 0; k < RB; ++k) {
+                  const int rr = r0 + k;
+                  if (!((wm >> rr) & 1u)) continue;            // warp-uniform
+                  float dz = tT[rr * 33 + lane];
+                  if (up_w) dz += tT[(rr ^ 1) * 33 + lane];
+                  if (up_h) { dz += tT[(rr ^ 8) * 33 + lane]; if (up_w) dz += tT[(rr ^ 9) * 33 + lane]; }
+                  const float x = xs[k];
+                  float du = dz;
+                  if (relu && !(fmaf(a, x, b) > 0.f)) du = 0.f;
+                  s1 += du; s2 += du * (x - ctr);
+                  float* q = db + rd[rr] + col;
+                  const float g = ga * du;
+                  if (atom) atomicAdd(q, g);
+                  else *q = qs[k] + g;
                 }
               }
+              if (E.s1) { atomicAdd(&st_[(2 * e) * p.BN + cb + lane], s1); atomicAdd(&st_[(2 * e + 1) * p.BN + cb + lane], s2); }
             }
           }
+          __syncwarp();
         }
+        (void)vmask;
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[ab]);
         if (any_s) {
@@ -683,7 +719,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   // ---- teardown
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -846,10 +882,10 @@ TcGeom tc_geom(const hdn_conv* c, int mode) {
   return g;
 }
 
-TcPlan tc_plan(const hdn_conv* c, const TcGeom& g, int mode) {
+TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   TcPlan pl;
   memset(&pl, 0, sizeof(pl));
-  pl.n_tiles = (g.NC + 255) / 256;
+  pl.n_tiles = (g.NC + 255) / 256 + extra_tiles;
   int bn = (g.NC + pl.n_tiles - 1) / pl.n_tiles;
   pl.BN = (bn + 15) / 16 * 16;
   const int nsrc = mode == 0 ? c->nsrc : 1;               // dgrad: the A operand is dY alone
@@ -879,21 +915,32 @@ TcPlan tc_plan(const hdn_conv* c, const TcGeom& g, int mode) {
   pl.raw_bytes = (off + 127) / 128 * 128;
   pl.tab_ints = toff;
   const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * pl.CK * 2;
-  int nsb = (int)((48 * 1024) / b_bytes);
-  pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
   int cols = 32;
   while (cols < 2 * pl.BN) cols *= 2;                      // two accumulator buffers
   pl.tmem_cols = cols;
   pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * pl.CK;
-  const size_t fixed = NSA * a_bytes + pl.nsb * b_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 +
-                       (2 * NSA + 2 * NSB_MAX + 4) * 8 + 16;
-  if (g.s2d) pl.nraw = 0;
-  else {
-    long long room = (long long)(226 * 1024) - (long long)fixed;
-    int nraw = (int)(room / pl.raw_bytes);
-    pl.nraw = nraw > NRAW_MAX ? NRAW_MAX : nraw;
+  const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES +
+                      (2 * NSA + 2 * NSB_MAX + 4) * 8 + 16;
+  const long long budget = 226 * 1024;
+  // raw fp32 ring: 3 stages when they fit next to two weight blocks, else 2; the weight ring takes what is left:
+  // every tile streams ALL its weight blocks from L2, so the bytes in flight there set the pace of narrow layers
+  pl.nraw = 0;
+  if (!g.s2d) {
+    pl.nraw = ((long long)(base + 2 * b_bytes + 3ull * pl.raw_bytes) <= budget) ? 3 : 2;
+    if ((long long)(base + 2 * b_bytes + (size_t)pl.nraw * pl.raw_bytes) > budget) pl.nraw = 0;   // does not fit: refused by tc_launch
   }
+  long long room = budget - (long long)base - (long long)pl.nraw * pl.raw_bytes;
+  int nsb = (int)(room / (long long)b_bytes);
+  pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
+  const size_t fixed = base + pl.nsb * b_bytes;
   pl.smem = fixed + (size_t)pl.nraw * pl.raw_bytes;
+  return pl;
+}
+
+// narrower column tiles until two raw stages and two weight blocks fit next to the rest
+TcPlan tc_plan(const hdn_conv* c, const TcGeom& g, int mode) {
+  TcPlan pl = tc_plan1(c, g, mode, 0);
+  for (int extra = 1; extra < 8 && !g.s2d && pl.nraw < 2; ++extra) pl = tc_plan1(c, g, mode, extra);
   return pl;
 }
 

@@ -76,16 +76,17 @@ struct TileC { int n_tile, n_img, d0, h0, w0; long long m0; };
 
 __device__ __forceinline__ TileC tile_decode(const TcParams& p, long long w) {
   TileC t;
-  t.n_tile = (int)(w / p.tiles);
-  long long r = w - (long long)t.n_tile * p.tiles;
+  const unsigned tiles = (unsigned)p.tiles;               // work items fit 32 bits (checked on the host)
+  t.n_tile = (int)((unsigned)w / tiles);
+  unsigned r = (unsigned)w - (unsigned)t.n_tile * tiles;
   t.n_img = t.d0 = t.h0 = t.w0 = 0; t.m0 = 0;
   if (p.flat) {
-    t.m0 = r * 128;
+    t.m0 = (long long)r * 128;
   } else {
-    const int tw_ = (int)(r % p.tiles_w); r /= p.tiles_w;
-    const int th_ = (int)(r % p.tiles_h); r /= p.tiles_h;
-    t.d0 = (int)(r % p.D); t.n_img = (int)(r / p.D);
-    t.h0 = th_ * 16; t.w0 = tw_ * 8;
+    const unsigned tw_ = r % (unsigned)p.tiles_w; r /= (unsigned)p.tiles_w;
+    const unsigned th_ = r % (unsigned)p.tiles_h; r /= (unsigned)p.tiles_h;
+    t.d0 = (int)(r % (unsigned)p.D); t.n_img = (int)(r / (unsigned)p.D);
+    t.h0 = (int)th_ * 16; t.w0 = (int)tw_ * 8;
   }
   return t;
 }
@@ -1024,6 +1025,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   const long long tiles = pl.flat ? (p.M + 127) / 128 : (long long)c->N * c->D * pl.tiles_h * pl.tiles_w;
   p.tiles = tiles;
   p.total_work = tiles * pl.n_tiles;
+  HDN_CHECK_ARG(p.total_work < (1ll << 31), "conv tc: too many work items");
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;

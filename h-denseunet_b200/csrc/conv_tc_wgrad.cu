@@ -37,6 +37,10 @@ struct WgParams {
   int pd_lo, ph_lo, pw_lo;     // padding in front of tap 0
   int s2d, s2d_quads;          // stride-2 stem in space-to-depth form (see conv_tc.cu); Cin here = 4 * quads
   int cin_real;                //   real input channels of the stem (<= 4)
+  // asynchronous producer (everything but the stems): raw fp32 ring and per-tile geometry tables
+  int nraw, raw_bytes, CW;     // CW: input channels per raw sub-stage (64, or 32 with two sources)
+  int PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2];
+  int tab_src[2], tab_vq[2], tab_dy, tab_ints;
   int tiles_w, tiles_h;
   long long n_pos_tiles;       // position tiles per slice set
   long long M;
@@ -122,6 +126,25 @@ __device__ __forceinline__ void stage_block(const hdn_src* src, int nsrc, const 
   }
 }
 
+__device__ __forceinline__ void wg_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void wg_store_chunks(uint8_t* dst, uint32_t ppad, int q, bool qok, int nchunks, float4 v0, float4 v1, int lane) {
+  const int l8 = lane & 7;
+  const bool even = (l8 & 1) == 0;
+  const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
+  const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
+  const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+  const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
+  const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  uint4 o;
+  if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }
+  else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }
+  if (qok && chunk < nchunks) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
+}
+constexpr int NTW = 3;         // geometry-table buffers
+constexpr int WTU = 3;         // transform: pixel groups fetched ahead per warp
+
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -129,9 +152,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   const uint32_t B_BYTES = (uint32_t)((p.BN + 7) / 8) * 129u * 16u;  // dY tile, BN channels x 128 pixels
   uint8_t* sA = smem;
   uint8_t* sB = sA + NS * A_BYTES;
-  int* offs = reinterpret_cast<int*>(sB + NS * B_BYTES);             // [NS][2*P + 128]
+  int* offs = reinterpret_cast<int*>(sB + NS * B_BYTES);             // [NS][2*P + 128]   (direct path)
   const int OFFS_PER = 2 * p.P + 128;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(offs + NS * OFFS_PER) + 15) & ~uintptr_t(15));
+  int* tabs = offs + NS * OFFS_PER;                                   // [NTW][tab_ints]   (asynchronous path)
+  uint8_t* sRaw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tabs + NTW * p.tab_ints) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRaw + (size_t)p.nraw * p.raw_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
   uint64_t* acc_full = bars + 2 * NS;
@@ -166,11 +191,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   // position-tile iteration (identical in every role): tile t -> (n, d, th, tw) or flat index
   auto tile_valid = [&](long long t, int& n_img, int& d0, int& h0, int& w0, long long& m0) -> bool {
     if (p.flat) { m0 = t * 128; n_img = d0 = h0 = w0 = 0; return true; }
-    long long r = t;
-    const int tw_ = (int)(r % p.tiles_w); r /= p.tiles_w;
-    const int th_ = (int)(r % p.tiles_h); r /= p.tiles_h;
-    d0 = (int)(r % p.D); n_img = (int)(r / p.D);
-    h0 = th_ * 16; w0 = tw_ * 8; m0 = 0;
+    unsigned r = (unsigned)t;                            // position tiles fit 32 bits (checked on the host)
+    const unsigned tw_ = r % (unsigned)p.tiles_w; r /= (unsigned)p.tiles_w;
+    const unsigned th_ = r % (unsigned)p.tiles_h; r /= (unsigned)p.tiles_h;
+    d0 = (int)(r % (unsigned)p.D); n_img = (int)(r / (unsigned)p.D);
+    h0 = (int)th_ * 16; w0 = (int)tw_ * 8; m0 = 0;
     const int vd = d0 - hd + gdz;
     return vd >= 0 && vd < p.D;                          // the group's depth slab lies outside: no contribution
   };
@@ -180,6 +205,212 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     int st = 0;
     uint32_t ph = 0;
     bool produced = false;
+    if (p.nraw >= 2) {
+      // ---- asynchronous path: raw fp32 sub-stages (64 channels of the patch, or 64 channels of the dY tile) are fetched
+      // with cp.async one sub-stage ahead, then transformed into the bf16 operand stage of the tile
+      const int l8 = lane & 7, pg = lane >> 3;
+      const int CW = p.CW, NQ = CW >> 2, NQs = (CW == 64) ? 4 : 3;
+      const int nA = (min(128, p.Cin - ci0) + CW - 1) / CW, nB = (p.BN + 63) >> 6, nsub = nA + nB;
+      const int climit = min(p.Cout, co0 + p.BN);
+      struct SubIt { long long t; int u, seq; bool done; int n_img, d0, h0, w0; long long m0; };
+      auto settle = [&](SubIt& it) {
+        while (it.t < p.n_pos_tiles && !tile_valid(it.t, it.n_img, it.d0, it.h0, it.w0, it.m0)) it.t += nsplit;
+        it.done = it.t >= p.n_pos_tiles;
+      };
+      auto advance = [&](SubIt& it) {
+        if (++it.u == nsub) { it.u = 0; it.t += nsplit; ++it.seq; settle(it); }
+      };
+      SubIt is, tr;
+      is.t = split; is.u = 0; is.seq = 0; settle(is);
+      tr = is;
+      int built_seq = -1;
+      auto build_tables = [&](const SubIt& it) {
+        int* tab = tabs + (it.seq % NTW) * p.tab_ints;
+        for (int s = 0; s < p.nsrc; ++s) {
+          const hdn_src& S = p.src[s];
+          const int vh0 = it.h0 - hh + gth0, vw0 = it.w0 - hw + gtw0;
+          const int sh0 = (S.uh == 2) ? (vh0 >> 1) : vh0, sw0 = (S.uw == 2) ? (vw0 >> 1) : vw0;
+          for (int i = tid; i < p.Ps[s]; i += WG_PROD) {
+            int off = -1;
+            if (p.flat) {
+              if (it.m0 + i < p.M) off = i * S.t.ldc;
+            } else {
+              const int sh = sh0 + i / p.PWs[s], sw = sw0 + i % p.PWs[s];
+              if (sh >= 0 && sh < S.H && sw >= 0 && sw < S.W) off = (sh * S.W + sw) * S.t.ldc;
+            }
+            tab[p.tab_src[s] + i] = off;
+          }
+          for (int q = tid; q < p.P; q += WG_PROD) {
+            int sq = -1;
+            if (p.flat) {
+              if (it.m0 + q < p.M) sq = q;
+            } else {
+              const int vh = vh0 + q / p.PW, vw = vw0 + q % p.PW;
+              if (vh >= 0 && vh < p.H && vw >= 0 && vw < p.W) {
+                const int sh = (S.uh == 2) ? (vh >> 1) : vh, sw = (S.uw == 2) ? (vw >> 1) : vw;
+                sq = (sh - sh0) * p.PWs[s] + (sw - sw0);
+              }
+            }
+            tab[p.tab_vq[s] + q] = sq;
+          }
+        }
+        for (int r = tid; r < 128; r += WG_PROD) {
+          int off = -1;
+          if (p.flat) {
+            if (it.m0 + r < p.M) off = r * p.dy.ldc;
+          } else {
+            const int oh = it.h0 + (r >> 3), ow = it.w0 + (r & 7);
+            if (oh < p.H && ow < p.W) off = (oh * p.W + ow) * p.dy.ldc;
+          }
+          tab[p.tab_dy + r] = off;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      };
+      auto issue = [&](const SubIt& it, int slot) {
+        if (it.seq != built_seq) { build_tables(it); built_seq = it.seq; }
+        const int* tab = tabs + (it.seq % NTW) * p.tab_ints;
+        uint8_t* raw = sRaw + (size_t)slot * p.raw_bytes;
+        if (it.u < nA) {
+          const int c0 = ci0 + it.u * CW;
+          for (int s = 0; s < p.nsrc; ++s) {
+            const hdn_src& S = p.src[s];
+            const float* base;
+            if (p.flat) base = S.t.p + it.m0 * S.t.ldc + S.t.coff;
+            else {
+              const int vd = it.d0 - hd + gdz;
+              const int sd = (S.ud == 2) ? (vd >> 1) : vd;
+              base = S.t.p + ((long long)it.n_img * S.D + sd) * S.H * S.W * S.t.ldc + S.t.coff;
+            }
+            const int* spix = tab + p.tab_src[s];
+            uint8_t* rs = raw + p.raw_off[s];
+            const int n16 = p.Ps[s] * NQ;
+            for (int i = tid; i < n16; i += WG_PROD) {
+              const int sq = i >> NQs, part = i & (NQ - 1);
+              const int off = spix[sq], c = c0 + part * 4;
+              if (off >= 0 && c < p.Cin) wg_cp_async16(rs + (size_t)i * 16, base + off + c);
+            }
+            if (tid < NQ && c0 + tid * 4 < p.Cin) {
+              if (S.pa) wg_cp_async16(raw + p.ab_off[s] + tid * 16, S.pa + c0 + tid * 4);
+              if (S.pb) wg_cp_async16(raw + p.ab_off[s] + CW * 4 + tid * 16, S.pb + c0 + tid * 4);
+            }
+          }
+        } else {
+          const int c0 = co0 + (it.u - nA) * 64;
+          const float* base = p.flat ? (p.dy.p + it.m0 * p.dy.ldc + p.dy.coff)
+                                     : (p.dy.p + ((long long)it.n_img * p.D + it.d0) * p.H * p.W * p.dy.ldc + p.dy.coff);
+          const int* dyo = tab + p.tab_dy;
+          for (int i = tid; i < 128 * 16; i += WG_PROD) {
+            const int q = i >> 4, part = i & 15;
+            const int off = dyo[q], c = c0 + part * 4;
+            if (off >= 0 && c < climit) wg_cp_async16(raw + (size_t)i * 16, base + off + c);
+          }
+        }
+      };
+      int slot_is = 0, slot_tr = 0;
+      for (int i = 0; i < p.nraw - 1; ++i) {
+        if (!is.done) { issue(is, slot_is); advance(is); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++slot_is == p.nraw) slot_is = 0;
+      }
+      while (!tr.done) {
+        if (p.nraw == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!is.done) { issue(is, slot_is); advance(is); }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (++slot_is == p.nraw) slot_is = 0;
+        if (tr.u == 0) { produced = true; tc::mbar_wait(&empty[st], ph ^ 1); }
+        const int* tab = tabs + (tr.seq % NTW) * p.tab_ints;
+        const uint8_t* raw = sRaw + (size_t)slot_tr * p.raw_bytes;
+        const int cA = l8 * 4, cB = 32 + l8 * 4;
+        if (tr.u < nA) {
+          const int c0 = ci0 + tr.u * CW;
+          const bool okA = cA < CW && c0 + cA < p.Cin, okB = cB < CW && c0 + cB < p.Cin;
+          uint8_t* dst = sA + st * A_BYTES + (uint32_t)tr.u * (uint32_t)(CW / 8) * p.Ppad * 16u;
+          float4 a0[2], b0[2], a1[2], b1[2];
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
+            b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s < p.nsrc) {
+              const float* ab = reinterpret_cast<const float*>(raw + p.ab_off[s]);
+              if (p.src[s].pa) { if (okA) a0[s] = *reinterpret_cast<const float4*>(ab + cA); if (okB) a1[s] = *reinterpret_cast<const float4*>(ab + cB); }
+              if (p.src[s].pb) { if (okA) b0[s] = *reinterpret_cast<const float4*>(ab + CW + cA); if (okB) b1[s] = *reinterpret_cast<const float4*>(ab + CW + cB); }
+            }
+          }
+          const float* rawf0 = reinterpret_cast<const float*>(raw + p.raw_off[0]);
+          const float* rawf1 = reinterpret_cast<const float*>(raw + p.raw_off[1]);
+          const int* vq0 = tab + p.tab_vq[0];
+          const int* vq1 = tab + p.tab_vq[1];
+          const int relu0 = p.src[0].relu, relu1 = p.nsrc > 1 ? p.src[1].relu : 0;
+          for (int q0 = warp * 4; q0 < p.P; q0 += 32 * WTU) {
+            int sq0[WTU], sq1[WTU];
+#pragma unroll
+            for (int u = 0; u < WTU; ++u) {
+              const int q = q0 + u * 32 + pg;
+              sq0[u] = sq1[u] = -1;
+              if (q < p.P) { sq0[u] = vq0[q]; if (p.nsrc > 1) sq1[u] = vq1[q]; }
+            }
+            float4 x0a[WTU], x0b[WTU], x1a[WTU], x1b[WTU];
+#pragma unroll
+            for (int u = 0; u < WTU; ++u) {
+              x0a[u] = x0b[u] = x1a[u] = x1b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (sq0[u] >= 0) {
+                const float* row = rawf0 + sq0[u] * CW;
+                if (okA) x0a[u] = *reinterpret_cast<const float4*>(row + cA);
+                if (okB) x0b[u] = *reinterpret_cast<const float4*>(row + cB);
+              }
+              if (sq1[u] >= 0) {
+                const float* row = rawf1 + sq1[u] * CW;
+                if (okA) x1a[u] = *reinterpret_cast<const float4*>(row + cA);
+                if (okB) x1b[u] = *reinterpret_cast<const float4*>(row + cB);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < WTU; ++u) {
+              if (q0 + u * 32 >= p.P) break;
+              const int q = q0 + u * 32 + pg;
+              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+              if (sq0[u] >= 0) {
+                if (okA) v0 = pro4(x0a[u], a0[0], b0[0], relu0);
+                if (okB) v1 = pro4(x0b[u], a1[0], b1[0], relu0);
+              }
+              if (sq1[u] >= 0) {
+                if (okA) { float4 t4 = pro4(x1a[u], a0[1], b0[1], relu1); v0.x += t4.x; v0.y += t4.y; v0.z += t4.z; v0.w += t4.w; }
+                if (okB) { float4 t4 = pro4(x1b[u], a1[1], b1[1], relu1); v1.x += t4.x; v1.y += t4.y; v1.z += t4.z; v1.w += t4.w; }
+              }
+              wg_store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, CW / 8, v0, v1, lane);
+            }
+          }
+        } else {
+          const int cb = (tr.u - nA) * 64;
+          const int c0 = co0 + cb;
+          const bool okA = c0 + cA < climit, okB = c0 + cB < climit;
+          uint8_t* dst = sB + st * B_BYTES + (uint32_t)(cb / 8) * 129u * 16u;
+          const int nch = (p.BN - cb + 7) / 8;
+          const int* dyo = tab + p.tab_dy;
+          const float* rawf = reinterpret_cast<const float*>(raw);
+#pragma unroll
+          for (int it4 = 0; it4 < 4; ++it4) {
+            const int q = it4 * 32 + warp * 4 + pg;            // 128 pixels = 4 x (8 warps x 4)
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (dyo[q] >= 0) {
+              if (okA) v0 = *reinterpret_cast<const float4*>(rawf + q * 64 + cA);
+              if (okB) v1 = *reinterpret_cast<const float4*>(rawf + q * 64 + cB);
+            }
+            wg_store_chunks(dst, 129u, q, true, nch, v0, v1, lane);
+          }
+        }
+        if (tr.u == nsub - 1) {
+          tc::fence_proxy_async_smem();
+          tc::mbar_arrive(&full[st]);
+          if (++st == NS) { st = 0; ph ^= 1; }
+        }
+        if (++slot_tr == p.nraw) slot_tr = 0;
+        advance(tr);
+      }
+    } else {
+    // ---- direct path (space-to-depth stems)
     for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
       int n_img, d0, h0, w0;
       long long m0;
@@ -255,6 +486,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
       if (++st == NS) { st = 0; ph ^= 1; }
+    }
+
     }
 
     // =================================================================== epilogue: TMEM -> dW (vector reductions)
@@ -343,6 +576,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 
 struct WgPlan {
   int BN, G, groups, ci_tiles, co_tiles, flat, PH, PW, P, Ppad, tiles_h, tiles_w, tmem_cols, row_mode;
+  int nraw, raw_bytes, CW, PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], tab_src[2], tab_vq[2], tab_dy, tab_ints;
   long long n_pos_tiles;
   size_t smem;
   int splits;
@@ -401,9 +635,36 @@ bool wg_plan(const hdn_conv* c, const WgGeom& gm, WgPlan& best) {
     while (cols_t < G * pl.BN) cols_t *= 2;
     pl.tmem_cols = cols_t;
     const size_t a_bytes = 16ull * pl.Ppad * 16, b_bytes = (size_t)((pl.BN + 7) / 8) * 129 * 16;
-    pl.smem = NS * (a_bytes + b_bytes) + NS * (2ull * pl.P + 128) * 4 + 16 + (2 * NS + 1) * 8 + 16;
-    if (pl.smem > 220 * 1024) continue;
-    const double cost = (double)pl.ci_tiles * pl.co_tiles * pl.groups * ((double)pl.P * 128 * c->nsrc + 128.0 * pl.BN);
+    // asynchronous producer geometry (not for the space-to-depth stems)
+    pl.CW = (c->nsrc == 2) ? 32 : 64;
+    int roff = 0, toff = 0;
+    for (int s = 0; s < 2; ++s) {
+      pl.PHs[s] = pl.PH; pl.PWs[s] = pl.PW;
+      if (s < c->nsrc && !gm.s2d && !flat) {
+        if (c->src[s].uh == 2) pl.PHs[s] = pl.PH / 2 + 1;
+        if (c->src[s].uw == 2) pl.PWs[s] = pl.PW / 2 + 1;
+      }
+      pl.Ps[s] = s < c->nsrc ? pl.PHs[s] * pl.PWs[s] : 0;
+      pl.raw_off[s] = roff; roff += pl.Ps[s] * pl.CW * 4;
+      pl.tab_src[s] = toff; toff += pl.Ps[s];
+      pl.tab_vq[s] = toff; toff += s < c->nsrc ? pl.P : 0;
+    }
+    for (int s = 0; s < 2; ++s) { pl.ab_off[s] = roff; roff += s < c->nsrc ? 2 * pl.CW * 4 : 0; }
+    if (roff < 128 * 256) roff = 128 * 256;              // a dY sub-stage: 128 pixels x 64 channels
+    pl.raw_bytes = (roff + 127) / 128 * 128;
+    pl.tab_dy = toff; toff += 128;
+    pl.tab_ints = toff;
+    const size_t fixed = NS * (a_bytes + b_bytes) + NS * (2ull * pl.P + 128) * 4 + (size_t)NTW * pl.tab_ints * 4 + 128 + 16 +
+                         (2 * NS + 1) * 8 + 16;
+    pl.nraw = 0;
+    if (!gm.s2d) {
+      if (fixed + 3ull * pl.raw_bytes <= 226 * 1024) pl.nraw = 3;
+      else if (fixed + 2ull * pl.raw_bytes <= 226 * 1024) pl.nraw = 2;
+    }
+    pl.smem = fixed + (size_t)pl.nraw * pl.raw_bytes;
+    if (pl.smem > 226 * 1024) continue;
+    double cost = (double)pl.ci_tiles * pl.co_tiles * pl.groups * ((double)pl.P * 128 * c->nsrc + 128.0 * pl.BN);
+    if (!gm.s2d && pl.nraw == 0) cost *= 4.0;            // falls back to the synchronous producer: much slower
     if (cost < best_cost) { best_cost = cost; best = pl; found = true; }
   }
   if (!found) return false;
@@ -464,6 +725,13 @@ int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.M = (long long)c->N * c->D * c->H * c->W;
   p.nsrc = c->nsrc; p.src[0] = c->src[0]; p.src[1] = c->src[1];
   p.dy = c->y; p.dw = dw; p.tmem_cols = pl.tmem_cols;
+  p.nraw = pl.nraw; p.raw_bytes = pl.raw_bytes; p.CW = pl.CW;
+  for (int s = 0; s < 2; ++s) {
+    p.PHs[s] = pl.PHs[s]; p.PWs[s] = pl.PWs[s]; p.Ps[s] = pl.Ps[s]; p.raw_off[s] = pl.raw_off[s]; p.ab_off[s] = pl.ab_off[s];
+    p.tab_src[s] = pl.tab_src[s]; p.tab_vq[s] = pl.tab_vq[s];
+  }
+  p.tab_dy = pl.tab_dy; p.tab_ints = pl.tab_ints;
+  HDN_CHECK_ARG(pl.n_pos_tiles < (1ll << 31), "conv_wgrad tc: too many position tiles");
   dim3 grid((unsigned)(pl.ci_tiles * pl.co_tiles * pl.groups), (unsigned)pl.splits);
   conv_wgrad_tc_kernel<<<grid, WG_THREADS, pl.smem, st>>>(p);
   HDN_CHECK_LAUNCH("conv_wgrad_tc");

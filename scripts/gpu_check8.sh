@@ -1,0 +1,7 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_tc.py -q --timeout 60 --timeout-method thread > gpurun_out/pytest_tc.log 2>&1; tail -15 gpurun_out/pytest_tc.log
+for c in 3dconv_up4 conv_up4 fianl_conv dense2_x2 dense2_x1 dense4_x1 dense4_x2 3ddense2_x2; do
+  for w in wgrad; do timeout 120 python scripts/prof_conv.py $c $w 3 2>&1 | tail -1; done
+done | tee gpurun_out/conv_times_wgrad.txt

@@ -248,9 +248,10 @@ def run_gpu(a):
         "gpu_launches": int(launches), "clocks": clocks, "loss": loss, "memory_gib": net.memory_bytes() / 2 ** 30,
     }
 
+    # roofline of the dominant kernel class, measured live with CUDA events (one extra instrumented step; every rank
+    # takes part because the data-parallel exchange inside the step is collective)
+    agg = profile_step(m, net, a.profile_steps)
     if rank == 0:
-        # roofline of the dominant kernel class, measured live with CUDA events (one extra instrumented step)
-        agg = profile_step(m, net, a.profile_steps)
         tot = sum(v[0] for v in agg.values())
         top = max(agg.items(), key=lambda kv: kv[1][0])
         k, (t, fl, n) = top

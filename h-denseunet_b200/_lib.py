@@ -26,7 +26,8 @@ def build(force=False, verbose=False):
         if all(os.path.getmtime(d) <= t for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs + ["-lcuda"]
+    extra = os.environ.get("HDN_NVCC_EXTRA", "").split()      # e.g. -DHDN_TC_TIMING (per-role cycle counters)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + srcs + ["-lcuda"]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=_CSRC)

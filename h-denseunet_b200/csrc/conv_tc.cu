@@ -24,6 +24,17 @@
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
+// -DHDN_TC_TIMING: per-role wait/work cycle counters of CTA 0, printed at kernel end (development aid)
+#ifdef HDN_TC_TIMING
+#define TT_DECL(n) long long n = 0
+#define TT_BEGIN long long tt__0 = clock64()
+#define TT_ADD(n) do { long long tt__1 = clock64(); n += tt__1 - tt__0; tt__0 = tt__1; } while (0)
+#else
+#define TT_DECL(n)
+#define TT_BEGIN
+#define TT_ADD(n)
+#endif
+
 namespace {
 
 constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
@@ -35,6 +46,8 @@ constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs < N
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
 constexpr int RB = 16;        // dgrad epilogue: rows fetched ahead per lane
+constexpr int MAXC0 = 12;     // copies per producer thread and stage, source 0 (180 px x 16 quads / 256 threads)
+constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 constexpr int TU = 3;         // transform: pixel groups looked up / fetched ahead per warp
 
 struct TcParams {
@@ -45,7 +58,7 @@ struct TcParams {
   int flat;                   // 1: rows are 128 consecutive linear positions (1x1x1, no up-sampling)
   int PH, PW, P, Ppad;        // virtual patch rows, cols, pixels, padded (odd) pixel count
   int PHs[2], PWs[2], Ps[2];  // source-resolution patch of each source
-  int raw_off[2], ab_off[2], raw_bytes;   // layout of one raw stage
+  int raw_off[2], ab_off[2], raw_bytes;   // layout of one raw stage (pixel stride CK + 4 floats: bank-conflict-free reads)
   int tab_src[2], tab_vq[2], tab_ints;    // layout of one geometry table
   int tiles_w, tiles_h;
   long long tiles, total_work;
@@ -280,23 +293,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       it_init(p, is);
       const int NQ = p.CK >> 2;                            // 16-byte quads per pixel in a raw stage (16 or 8)
       const int NQs = (p.CK == 64) ? 4 : 3;
+      const int RS = p.CK + 4, RSB = RS * 4;               // raw pixel stride in floats / bytes
+      // Copy list of this thread for the tile the copy front is on, kept in registers: item j moves the 16 bytes at
+      // element offset goff[j] (from the slab base + channel block) to raw-slot byte (ptid + 256*j)*16.  Rebuilt once
+      // per tile, so a stage costs a handful of instructions per copy.
+      int goff0[MAXC0], goff1[MAXC1];
+      const int part4 = (ptid & (NQ - 1)) * 4;             // this thread's channel quad inside the stage (256 % NQ == 0)
       auto issue = [&](const StageIt& it, int slot) {
-        if (it.seq != built_seq) { build_tables(it); built_seq = it.seq; }
-        const int* tab = tabs + (it.seq % NTAB) * p.tab_ints;
+        if (it.seq != built_seq) {
+          build_tables(it);
+          built_seq = it.seq;
+          const int* tab = tabs + (it.seq % NTAB) * p.tab_ints;
+          const int n0 = p.Ps[0] * NQ, n1 = p.nsrc > 1 ? p.Ps[1] * NQ : 0;
+#pragma unroll
+          for (int j = 0; j < MAXC0; ++j) {
+            const int i = ptid + j * NPROD;
+            int g = -1;
+            if (i < n0) { const int o = tab[p.tab_src[0] + (i >> NQs)]; if (o >= 0) g = o + part4; }
+            goff0[j] = g;
+          }
+#pragma unroll
+          for (int j = 0; j < MAXC1; ++j) {
+            const int i = ptid + j * NPROD;
+            int g = -1;
+            if (i < n1) { const int o = tab[p.tab_src[1] + (i >> NQs)]; if (o >= 0) g = o + part4; }
+            goff1[j] = g;
+          }
+        }
         uint8_t* raw = sRaw + (size_t)slot * p.raw_bytes;
         const int c0 = it.kb * p.CK;
-        for (int s = 0; s < p.nsrc; ++s) {
-          const hdn_src& S = p.src[s];
-          const float* base = slab_base(it, s);
-          const int* spix = tab + p.tab_src[s];
-          uint8_t* rs = raw + p.raw_off[s];
-          const int n16 = p.Ps[s] * NQ;
-          for (int i = ptid; i < n16; i += NPROD) {
-            const int sq = i >> NQs, part = i & (NQ - 1);
-            const int off = spix[sq], c = c0 + part * 4;
-            if (off >= 0 && c < p.K) cp_async16(rs + (size_t)i * 16, base + off + c);
+        const bool cok = c0 + part4 < p.K;
+        // item j = 16 bytes of source pixel (ptid + 256 j) >> NQs, quad ptid & (NQ-1); raw pixel stride (CK + 4) floats
+        const uint32_t d0 = (uint32_t)(ptid >> NQs) * (uint32_t)RSB + (uint32_t)part4 * 4u, dj = (uint32_t)(NPROD >> NQs) * (uint32_t)RSB;
+        {
+          const float* base = slab_base(it, 0) + c0;
+          uint8_t* rs = raw + p.raw_off[0] + d0;
+          if (cok) {
+#pragma unroll
+            for (int j = 0; j < MAXC0; ++j)
+              if (goff0[j] >= 0) cp_async16(rs + j * dj, base + goff0[j]);
           }
-          if (ptid < NQ && c0 + ptid * 4 < p.K) {
+        }
+        if (p.nsrc > 1) {
+          const float* base = slab_base(it, 1) + c0;
+          uint8_t* rs = raw + p.raw_off[1] + d0;
+          if (cok) {
+#pragma unroll
+            for (int j = 0; j < MAXC1; ++j)
+              if (goff1[j] >= 0) cp_async16(rs + j * dj, base + goff1[j]);
+          }
+        }
+        if (ptid < NQ && cok) {
+          for (int s = 0; s < p.nsrc; ++s) {
+            const hdn_src& S = p.src[s];
             if (S.pa) cp_async16(raw + p.ab_off[s] + ptid * 16, S.pa + c0 + ptid * 4);
             if (S.pb) cp_async16(raw + p.ab_off[s] + p.CK * 4 + ptid * 16, S.pb + c0 + ptid * 4);
           }
@@ -308,74 +357,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         cp_async_commit();
         if (++slot_is == p.nraw) slot_is = 0;
       }
+      TT_DECL(t_cp); TT_DECL(t_bar); TT_DECL(t_issue); TT_DECL(t_aempty); TT_DECL(t_xform); TT_DECL(n_stage);
       while (!tr.done) {
+        TT_BEGIN;
         cp_async_wait(p.nraw - 2);                         // this thread's copies of stage `tr` have landed
+        TT_ADD(t_cp);
         bar_producers();                                   // ... and everyone else's; everyone is also done reading the slot refilled next
+        TT_ADD(t_bar);
         if (!is.done) { issue(is, slot_is); it_next(p, is); }
         cp_async_commit();
         if (++slot_is == p.nraw) slot_is = 0;
+        TT_ADD(t_issue);
         tc::mbar_wait(&a_empty[sa], pha ^ 1);
+        TT_ADD(t_aempty);
         {
           const int* tab = tabs + (tr.seq % NTAB) * p.tab_ints;
           const uint8_t* raw = sRaw + (size_t)slot_tr * p.raw_bytes;
           uint8_t* dst = sA + sa * A_BYTES;
           const int c0 = tr.kb * p.CK;
-          const int cA = l8 * 4, cB = 32 + l8 * 4;         // channel quads of this lane inside the stage
-          const bool okA = cA < p.CK && c0 + cA < p.K, okB = cB < p.CK && c0 + cB < p.K;
-          float4 a0[2], b0[2], a1[2], b1[2];
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
-            b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s < p.nsrc) {
-              const float* ab = reinterpret_cast<const float*>(raw + p.ab_off[s]);
-              if (p.src[s].pa) { if (okA) a0[s] = *reinterpret_cast<const float4*>(ab + cA); if (okB) a1[s] = *reinterpret_cast<const float4*>(ab + cB); }
-              if (p.src[s].pb) { if (okA) b0[s] = *reinterpret_cast<const float4*>(ab + p.CK + cA); if (okB) b1[s] = *reinterpret_cast<const float4*>(ab + p.CK + cB); }
-            }
-          }
-          // TU pixel groups per warp are looked up and fetched before any is processed (latency overlap)
+          // lane = patch pixel, inner loop over the 8-channel chunks: two 16-byte reads (conflict-free thanks to the
+          // padded pixel stride), BN/Scale/ReLU with warp-uniform (a, b), one 16-byte store per chunk, no shuffles.
           const float* rawf0 = reinterpret_cast<const float*>(raw + p.raw_off[0]);
           const float* rawf1 = reinterpret_cast<const float*>(raw + p.raw_off[1]);
+          const float* ab0 = reinterpret_cast<const float*>(raw + p.ab_off[0]);
+          const float* ab1 = reinterpret_cast<const float*>(raw + p.ab_off[1]);
           const int* vq0 = tab + p.tab_vq[0];
           const int* vq1 = tab + p.tab_vq[1];
-          const int relu0 = p.src[0].relu, relu1 = p.nsrc > 1 ? p.src[1].relu : 0;
-          for (int q0 = warp * 4; q0 < p.P; q0 += 32 * TU) {
-            int sq0[TU], sq1[TU];
+          const bool two = p.nsrc > 1;
+          const bool pa0 = p.src[0].pa != nullptr, pb0 = p.src[0].pb != nullptr, relu0 = p.src[0].relu != 0;
+          const bool pa1 = two && p.src[1].pa != nullptr, pb1 = two && p.src[1].pb != nullptr, relu1 = two && p.src[1].relu != 0;
+          const int nch = p.CK >> 3, nhalf = nch >> 1;           // chunks per stage (8 or 4); a work item = 32 pixels x half of them
+          const int nitems = ((p.P + 31) >> 5) * 2;
+          for (int item = warp; item < nitems; item += 8) {
+            const int q = (item >> 1) * 32 + lane;
+            const int j0 = (item & 1) * nhalf;
+            const bool qok = q < p.P;
+            const int sq0 = qok ? vq0[q] : -1;
+            const int sq1 = (qok && two) ? vq1[q] : -1;
+            const float* row0 = rawf0 + sq0 * RS;
+            const float* row1 = rawf1 + sq1 * RS;
+            uint8_t* drow = dst + (uint32_t)q * 16u;
 #pragma unroll
-            for (int u = 0; u < TU; ++u) {
-              const int q = q0 + u * 32 + pg;
-              sq0[u] = sq1[u] = -1;
-              if (q < p.P) { sq0[u] = vq0[q]; if (p.nsrc > 1) sq1[u] = vq1[q]; }
-            }
-            float4 x0a[TU], x0b[TU], x1a[TU], x1b[TU];
-#pragma unroll
-            for (int u = 0; u < TU; ++u) {
-              x0a[u] = x0b[u] = x1a[u] = x1b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (sq0[u] >= 0) {
-                const float* row = rawf0 + sq0[u] * p.CK;
-                if (okA) x0a[u] = *reinterpret_cast<const float4*>(row + cA);
-                if (okB) x0b[u] = *reinterpret_cast<const float4*>(row + cB);
+            for (int jj = 0; jj < 4; ++jj) {
+              if (jj >= nhalf) break;
+              const int j = j0 + jj, c = j * 8;
+              float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+              if (c0 + c < p.K) {                                  // warp-uniform
+                if (sq0 >= 0) {                                    // zero padding is applied AFTER BN/Scale/ReLU
+                  va = *reinterpret_cast<const float4*>(row0 + c);
+                  vb = *reinterpret_cast<const float4*>(row0 + c + 4);
+                  if (pa0 | pb0 | relu0) {
+                    const float4 aa = pa0 ? *reinterpret_cast<const float4*>(ab0 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ab_ = pa0 ? *reinterpret_cast<const float4*>(ab0 + c + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ba = pb0 ? *reinterpret_cast<const float4*>(ab0 + p.CK + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 bb = pb0 ? *reinterpret_cast<const float4*>(ab0 + p.CK + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    va = prologue4(va, aa, ba, relu0);
+                    vb = prologue4(vb, ab_, bb, relu0);
+                  }
+                }
+                if (sq1 >= 0) {
+                  float4 ua = *reinterpret_cast<const float4*>(row1 + c), ub = *reinterpret_cast<const float4*>(row1 + c + 4);
+                  if (pa1 | pb1 | relu1) {
+                    const float4 aa = pa1 ? *reinterpret_cast<const float4*>(ab1 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ab_ = pa1 ? *reinterpret_cast<const float4*>(ab1 + c + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ba = pb1 ? *reinterpret_cast<const float4*>(ab1 + p.CK + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 bb = pb1 ? *reinterpret_cast<const float4*>(ab1 + p.CK + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ua = prologue4(ua, aa, ba, relu1);
+                    ub = prologue4(ub, ab_, bb, relu1);
+                  }
+                  va.x += ua.x; va.y += ua.y; va.z += ua.z; va.w += ua.w;
+                  vb.x += ub.x; vb.y += ub.y; vb.z += ub.z; vb.w += ub.w;
+                }
               }
-              if (sq1[u] >= 0) {
-                const float* row = rawf1 + sq1[u] * p.CK;
-                if (okA) x1a[u] = *reinterpret_cast<const float4*>(row + cA);
-                if (okB) x1b[u] = *reinterpret_cast<const float4*>(row + cB);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < TU; ++u) {
-              if (q0 + u * 32 >= p.P) break;                 // warp-uniform
-              const int q = q0 + u * 32 + pg;
-              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-              if (sq0[u] >= 0) {                             // zero padding is applied AFTER BN/Scale/ReLU
-                if (okA) v0 = prologue4(x0a[u], a0[0], b0[0], relu0);
-                if (okB) v1 = prologue4(x0b[u], a1[0], b1[0], relu0);
-              }
-              if (sq1[u] >= 0) {
-                if (okA) { float4 t = prologue4(x1a[u], a0[1], b0[1], relu1); v0.x += t.x; v0.y += t.y; v0.z += t.z; v0.w += t.w; }
-                if (okB) { float4 t = prologue4(x1b[u], a1[1], b1[1], relu1); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
-              }
-              store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, v0, v1, lane);
+              uint4 o;
+              o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
+              o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+              if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)j * (uint32_t)p.Ppad * 16u) = o;
             }
           }
         }
@@ -384,7 +441,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++sa == NSA) { sa = 0; pha ^= 1; }
         if (++slot_tr == p.nraw) slot_tr = 0;
         it_next(p, tr);
+        TT_ADD(t_xform);
+#ifdef HDN_TC_TIMING
+        ++n_stage;
+#endif
       }
+#ifdef HDN_TC_TIMING
+      if (blockIdx.x == 0 && (tid == 0 || tid == 255))
+        printf("[prod t%d] stages %lld  cp_wait %lld  bar %lld  issue %lld  a_empty %lld  transform %lld (cycles/stage)\n", tid, n_stage,
+               t_cp / n_stage, t_bar / n_stage, t_issue / n_stage, t_aempty / n_stage, t_xform / n_stage);
+#endif
     } else {
       // ---- direct path (space-to-depth stems): register loads, UB pixel groups in flight per warp
       const bool okA = l8 < p.s2d_quads;
@@ -433,12 +499,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t phb = 0;
       const size_t blk = (size_t)p.BN * p.CK;
       while (!it.done) {
-        const __nv_bfloat16* wp = p.wpack + (size_t)it.t.n_tile * p.KB * T * blk;
-        for (int t2 = 0; t2 < taps_hw; ++t2) {
-          const int tap = it.dz * taps_hw + t2;
-          tc::mbar_wait_sleep(&b_empty[sb], phb ^ 1);
+        const __nv_bfloat16* src = p.wpack + (((size_t)it.t.n_tile * p.KB + it.kb) * T + (size_t)it.dz * taps_hw) * blk;
+        for (int t2 = 0; t2 < taps_hw; ++t2, src += blk) {
+          tc::mbar_wait(&b_empty[sb], phb ^ 1);
           tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
-          tc::bulk_g2s(sB + sb * B_BYTES, wp + ((size_t)it.kb * T + tap) * blk, B_BYTES, &b_full[sb]);
+          tc::bulk_g2s(sB + sb * B_BYTES, src, B_BYTES, &b_full[sb]);
           if (++sb == p.nsb) { sb = 0; phb ^= 1; }
         }
         it_next(p, it);
@@ -456,7 +521,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t pha = 0, phb = 0;
       int cur_seq = -1;
       uint32_t acc = 0, tmem_d = tmem_base;
+      const uint64_t adesc_hi = tc::make_smem_desc(0, lbo_a, sbo_a), bdesc_hi = tc::make_smem_desc(0, lbo_b, sbo_b);
+      const uint64_t kstep_a = (uint64_t)((2u * lbo_a) >> 4), kstep_b = (uint64_t)((2u * lbo_b) >> 4);
+      TT_DECL(t_acc); TT_DECL(t_afull); TT_DECL(t_bfull); TT_DECL(t_mma); TT_DECL(n_st);
       while (!it.done) {
+        TT_BEGIN;
         if (it.seq != cur_seq) {                            // first stage of a new tile: claim an accumulator buffer
           cur_seq = it.seq;
           const int ab = cur_seq & 1;
@@ -467,30 +536,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         const int cv = min(p.CK, p.K - it.kb * p.CK);
         const int nk = (cv + 15) >> 4;
+        TT_ADD(t_acc);
         tc::mbar_wait(&a_full[sa], pha);
         tc::tc_fence_after();
-        const uint32_t a_stage = tc::smem_u32(sA + sa * A_BYTES);
+        TT_ADD(t_afull);
+        // The issuing thread is a single serial instruction stream sharing its scheduler with producer warps: keep it
+        // to a handful of instructions per MMA.  Descriptors differ only in the 14-bit start-address field (16-byte
+        // units, < 2^14 for 227 KB of shared memory), so they are advanced by integer adds on the low word.
+        const uint64_t a_desc0 = adesc_hi | (uint64_t)((tc::smem_u32(sA + sa * A_BYTES) >> 4) & 0x3FFF);
+        uint32_t tap_units = 0;                              // (th * PW + tw) in 16-byte units
+        int twc = 0;
         for (int t2 = 0; t2 < taps_hw; ++t2) {
-          const int th = t2 / p.kw, tw = t2 - th * p.kw;
           tc::mbar_wait(&b_full[sb], phb);
           tc::tc_fence_after();
-          const uint32_t a_base = a_stage + (uint32_t)(th * p.PW + tw) * 16u;
-          const uint32_t b_base = tc::smem_u32(sB + sb * B_BYTES);
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t ad = tc::make_smem_desc(a_base + (uint32_t)k * 2u * lbo_a, lbo_a, sbo_a);
-            const uint64_t bd = tc::make_smem_desc(b_base + (uint32_t)k * 2u * lbo_b, lbo_b, sbo_b);
-            tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
-            acc = 1;
-          }
+          TT_ADD(t_bfull);
+          const uint64_t ad = a_desc0 + tap_units;
+          const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
+          tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
+          if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
+          if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
+          if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
+          acc = 1;
           tc::umma_commit(&b_empty[sb]);
           if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+          if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;
+          TT_ADD(t_mma);
         }
         tc::umma_commit(&a_empty[sa]);
         if (++sa == NSA) { sa = 0; pha ^= 1; }
         const int seq_before = it.seq;
         it_next(p, it);
         if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
+        TT_ADD(t_mma);
+#ifdef HDN_TC_TIMING
+        ++n_st;
+#endif
       }
+#ifdef HDN_TC_TIMING
+      if (blockIdx.x == 0)
+        printf("[mma] stages %lld  acc_empty %lld  a_full %lld  b_full %lld  issue %lld (cycles/stage)\n", n_st, t_acc / n_st, t_afull / n_st,
+               t_bfull / n_st, t_mma / n_st);
+#endif
     }
   } else {
     // =================================================================== epilogue (warps 10-13)
@@ -505,6 +591,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int hr = row >> 3, wr = row & 7;
     int seq = 0;
     float v[16];
+#ifdef HDN_TC_TIMING
+    long long te_wait = 0, te_work = 0;
+#endif
     for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++seq) {
       const TileC t = tile_decode(p, w);
       const int ab = seq & 1;
@@ -529,8 +618,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int i = etid; i < 4 * p.BN; i += 128) st_[i] = 0.f;
         bar_epilogue();
       }
+#ifdef HDN_TC_TIMING
+      long long te0 = clock64();
+#endif
       tc::mbar_wait_sleep(&acc_full[ab], (uint32_t)(seq >> 1) & 1u);
       tc::tc_fence_after();
+#ifdef HDN_TC_TIMING
+      te_wait += clock64() - te0; te0 = clock64();
+#endif
       const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * p.BN);
 
       if (p.mode == 0) {
@@ -714,7 +809,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
         }
       }
+#ifdef HDN_TC_TIMING
+      te_work += clock64() - te0;
+#endif
     }
+#ifdef HDN_TC_TIMING
+    if (blockIdx.x == 0 && etid == 0) printf("[epi] tiles %d  wait %lld  work %lld (cycles/tile)\n", seq, te_wait / max(seq, 1), te_work / max(seq, 1));
+#endif
   }
 
   // ---- teardown
@@ -908,7 +1009,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
     }
     pl.Ps[s] = s < nsrc ? pl.PHs[s] * pl.PWs[s] : 0;
     pl.raw_off[s] = off;
-    off += pl.Ps[s] * pl.CK * 4;
+    off += pl.Ps[s] * (pl.CK + 4) * 4;
     pl.tab_src[s] = toff; toff += pl.Ps[s];
     pl.tab_vq[s] = toff; toff += s < nsrc ? pl.P : 0;
   }

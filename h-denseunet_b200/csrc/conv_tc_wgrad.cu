@@ -541,22 +541,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       const uint32_t b_lbo = 128u, b_sbo = 129u * 16u;
       int st = 0;
       uint32_t ph = 0, acc = 0;
+      const uint64_t adesc_hi = tc::make_smem_desc(0, a_lbo, a_sbo), bdesc_hi = tc::make_smem_desc(0, b_lbo, b_sbo);
+      const int row2 = 2 * p.PW;                             // two patch rows (= 16 pixels of the tile) per K step, 16-byte units
+      // first tap of the group relative to the group's patch
+      const int t20 = tap0 % taps_hw;
+      const int twc0 = (p.G == 1) ? 0 : (t20 % p.kw);
+      const uint32_t tap_units0 = (uint32_t)((t20 / p.kw - gth0) * p.PW + (t20 % p.kw - gtw0));
       for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
         int n_img, d0, h0, w0;
         long long m0;
         if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
         tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
-        const uint32_t a_stage = tc::smem_u32(sA + st * A_BYTES);
-        const uint32_t b_stage = tc::smem_u32(sB + st * B_BYTES);
-        for (int g = 0; g < p.G; ++g) {
-          const int t2 = (tap0 + g) % taps_hw;
-          const int th = t2 / p.kw - gth0, tw = t2 % p.kw - gtw0;     // relative to the group's patch
-          for (int r = 0; r < 8; ++r) {
-            const uint64_t ad = tc::make_smem_desc(a_stage + (uint32_t)((th + 2 * r) * p.PW + tw) * 16u, a_lbo, a_sbo);
-            const uint64_t bd = tc::make_smem_desc(b_stage + (uint32_t)r * 256u, b_lbo, b_sbo);
-            tc::umma_bf16(tmem_base + (uint32_t)(g * p.BN), ad, bd, idesc, (acc | (uint32_t)(r > 0)));   // overwrite only on the very first K step of each tap
-          }
+        // lean issue loop (one serial thread): descriptors are advanced by integer adds on the 14-bit start-address field
+        const uint64_t ad0 = adesc_hi | (uint64_t)((tc::smem_u32(sA + st * A_BYTES) >> 4) & 0x3FFF);
+        const uint64_t bd0 = bdesc_hi | (uint64_t)((tc::smem_u32(sB + st * B_BYTES) >> 4) & 0x3FFF);
+        uint32_t tap_units = tap_units0;                     // ((th - gth0) * PW + (tw - gtw0)) in 16-byte units
+        int twc = twc0;
+        uint32_t tm = tmem_base;
+        for (int g = 0; g < p.G; ++g, tm += (uint32_t)p.BN) {
+          const uint64_t ad = ad0 + tap_units;
+          tc::umma_bf16(tm, ad, bd0, idesc, acc);            // overwrite only on the very first K step of each tap
+#pragma unroll
+          for (int r = 1; r < 8; ++r) tc::umma_bf16(tm, ad + (uint64_t)(r * row2), bd0 + (uint64_t)(r * 16), idesc, 1u);
+          if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;
         }
         acc = 1;
         tc::umma_commit(&empty[st]);

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_tc.py -q --timeout 60 --timeout-method thread 2>&1 | tail -3
+for c in 3dconv_up4 fianl_conv dense2_x2 dense2_x1 dense4_x1 3ddense2_x2; do
+  for w in fprop dgrad wgrad; do timeout 120 python scripts/prof_conv.py $c $w 3 2>&1 | tail -1; done
+done | tee gpurun_out/conv_times_v3.txt
+timeout 600 python bench.py --batch 1 --steps 2 --warmup 3 --no-cpu 2>&1 | tail -1 > gpurun_out/bench_512x48_b1.json; cut -c1-200 gpurun_out/bench_512x48_b1.json

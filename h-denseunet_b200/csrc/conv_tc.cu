@@ -45,7 +45,7 @@ constexpr int NRAW_MAX = 4;   // raw fp32 patch ring depth upper bound
 constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs < NRAW_MAX tiles ahead of the transform)
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
-constexpr int RB = 16;        // dgrad epilogue: rows fetched ahead per lane
+constexpr int RB = 32;        // dgrad epilogue: rows fetched ahead per lane
 constexpr int MAXC0 = 12;     // copies per producer thread and stage, source 0 (180 px x 16 quads / 256 threads)
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 constexpr int TU = 3;         // transform: pixel groups looked up / fetched ahead per warp
@@ -756,17 +756,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const long long* rd = rod + e * 32;
               const unsigned wm = wmask[e];
               float s1 = 0.f, s2 = 0.f;
-              // rows in batches of RB: all stored values (and old gradients) of a batch are requested before any is used
+              // rows in batches of RB: all stored values of a batch are requested before any is used; an accumulating
+              // write is a fire-and-forget reduction (RED.ADD executes in L2: no read latency on the SM side)
               for (int r0 = 0; r0 < 32; r0 += RB) {
-                if (!((wm >> r0) & ((1u << RB) - 1u))) continue;   // warp-uniform: no writer row in this batch
-                float xs[RB], qs[RB];
+                const unsigned bm = (RB == 32) ? wm : ((wm >> r0) & ((1u << (RB & 31)) - 1u));
+                if (!bm) continue;                               // warp-uniform: no writer row in this batch
+                float xs[RB];
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
-                  xs[k] = 0.f; qs[k] = 0.f;
-                  if ((wm >> (r0 + k)) & 1u) {
-                    xs[k] = __ldg(xb + rx[r0 + k] + col);
-                    if (acc && !atom) qs[k] = __ldcg(db + rd[r0 + k] + col);
-                  }
+                  xs[k] = 0.f;
+                  if ((wm >> (r0 + k)) & 1u) xs[k] = __ldg(xb + rx[r0 + k] + col);
                 }
 #pragma unroll
                 for (int k = 0; k < RB; ++k) {
@@ -781,8 +780,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   s1 += du; s2 += du * (x - ctr);
                   float* q = db + rd[rr] + col;
                   const float g = ga * du;
-                  if (atom) atomicAdd(q, g);
-                  else *q = qs[k] + g;
+                  if (atom | acc) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(g) : "memory");
+                  else *q = g;
                 }
               }
               if (E.s1) { atomicAdd(&st_[(2 * e) * p.BN + cb + lane], s1); atomicAdd(&st_[(2 * e + 1) * p.BN + cb + lane], s2); }

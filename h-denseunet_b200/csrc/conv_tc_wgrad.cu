@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       // ---- asynchronous path: raw fp32 sub-stages (64 channels of the patch, or 64 channels of the dY tile) are fetched
       // with cp.async one sub-stage ahead, then transformed into the bf16 operand stage of the tile
       const int l8 = lane & 7, pg = lane >> 3;
-      const int CW = p.CW, NQ = CW >> 2, NQs = (CW == 64) ? 4 : 3;
+      const int CW = p.CW, NQ = CW >> 2, NQs = (CW == 64) ? 4 : 3, RS = CW + 4;   // RS: raw pixel stride (floats), padded
       const int nA = (min(128, p.Cin - ci0) + CW - 1) / CW, nB = (p.BN + 63) >> 6, nsub = nA + nB;
       const int climit = min(p.Cout, co0 + p.BN);
       struct SubIt { long long t; int u, seq; bool done; int n_img, d0, h0, w0; long long m0; };
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             for (int i = tid; i < n16; i += WG_PROD) {
               const int sq = i >> NQs, part = i & (NQ - 1);
               const int off = spix[sq], c = c0 + part * 4;
-              if (off >= 0 && c < p.Cin) wg_cp_async16(rs + (size_t)i * 16, base + off + c);
+              if (off >= 0 && c < p.Cin) wg_cp_async16(rs + (size_t)sq * (RS * 4) + part * 16, base + off + c);
             }
             if (tid < NQ && c0 + tid * 4 < p.Cin) {
               if (S.pa) wg_cp_async16(raw + p.ab_off[s] + tid * 16, S.pa + c0 + tid * 4);
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           for (int i = tid; i < 128 * 16; i += WG_PROD) {
             const int q = i >> 4, part = i & 15;
             const int off = dyo[q], c = c0 + part * 4;
-            if (off >= 0 && c < climit) wg_cp_async16(raw + (size_t)i * 16, base + off + c);
+            if (off >= 0 && c < climit) wg_cp_async16(raw + (size_t)q * (68 * 4) + part * 16, base + off + c);
           }
         }
       };
@@ -322,83 +322,92 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         if (tr.u == 0) { produced = true; tc::mbar_wait(&empty[st], ph ^ 1); }
         const int* tab = tabs + (tr.seq % NTW) * p.tab_ints;
         const uint8_t* raw = sRaw + (size_t)slot_tr * p.raw_bytes;
-        const int cA = l8 * 4, cB = 32 + l8 * 4;
         if (tr.u < nA) {
+          // lane = patch pixel, inner loop over the 8-channel chunks of this sub-stage (see conv_tc.cu)
           const int c0 = ci0 + tr.u * CW;
-          const bool okA = cA < CW && c0 + cA < p.Cin, okB = cB < CW && c0 + cB < p.Cin;
           uint8_t* dst = sA + st * A_BYTES + (uint32_t)tr.u * (uint32_t)(CW / 8) * p.Ppad * 16u;
-          float4 a0[2], b0[2], a1[2], b1[2];
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            a0[s] = a1[s] = make_float4(1.f, 1.f, 1.f, 1.f);
-            b0[s] = b1[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (s < p.nsrc) {
-              const float* ab = reinterpret_cast<const float*>(raw + p.ab_off[s]);
-              if (p.src[s].pa) { if (okA) a0[s] = *reinterpret_cast<const float4*>(ab + cA); if (okB) a1[s] = *reinterpret_cast<const float4*>(ab + cB); }
-              if (p.src[s].pb) { if (okA) b0[s] = *reinterpret_cast<const float4*>(ab + CW + cA); if (okB) b1[s] = *reinterpret_cast<const float4*>(ab + CW + cB); }
-            }
-          }
           const float* rawf0 = reinterpret_cast<const float*>(raw + p.raw_off[0]);
           const float* rawf1 = reinterpret_cast<const float*>(raw + p.raw_off[1]);
+          const float* ab0 = reinterpret_cast<const float*>(raw + p.ab_off[0]);
+          const float* ab1 = reinterpret_cast<const float*>(raw + p.ab_off[1]);
           const int* vq0 = tab + p.tab_vq[0];
           const int* vq1 = tab + p.tab_vq[1];
-          const int relu0 = p.src[0].relu, relu1 = p.nsrc > 1 ? p.src[1].relu : 0;
-          for (int q0 = warp * 4; q0 < p.P; q0 += 32 * WTU) {
-            int sq0[WTU], sq1[WTU];
+          const bool two = p.nsrc > 1;
+          const bool pa0 = p.src[0].pa != nullptr, pb0 = p.src[0].pb != nullptr;
+          const int relu0 = p.src[0].relu;
+          const bool pa1 = two && p.src[1].pa != nullptr, pb1 = two && p.src[1].pb != nullptr;
+          const int relu1 = two ? p.src[1].relu : 0;
+          const int nhalf = CW >> 4;                             // chunks per work item (half of the sub-stage's chunks)
+          const int nitems = ((p.P + 31) >> 5) * 2;
+          for (int item = warp; item < nitems; item += 8) {
+            const int q = (item >> 1) * 32 + lane;
+            const int j0 = (item & 1) * nhalf;
+            const bool qok = q < p.P;
+            const int sq0 = qok ? vq0[q] : -1;
+            const int sq1 = (qok && two) ? vq1[q] : -1;
+            const float* row0 = rawf0 + sq0 * RS;
+            const float* row1 = rawf1 + sq1 * RS;
+            uint8_t* drow = dst + (uint32_t)q * 16u;
 #pragma unroll
-            for (int u = 0; u < WTU; ++u) {
-              const int q = q0 + u * 32 + pg;
-              sq0[u] = sq1[u] = -1;
-              if (q < p.P) { sq0[u] = vq0[q]; if (p.nsrc > 1) sq1[u] = vq1[q]; }
-            }
-            float4 x0a[WTU], x0b[WTU], x1a[WTU], x1b[WTU];
-#pragma unroll
-            for (int u = 0; u < WTU; ++u) {
-              x0a[u] = x0b[u] = x1a[u] = x1b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (sq0[u] >= 0) {
-                const float* row = rawf0 + sq0[u] * CW;
-                if (okA) x0a[u] = *reinterpret_cast<const float4*>(row + cA);
-                if (okB) x0b[u] = *reinterpret_cast<const float4*>(row + cB);
+            for (int jj = 0; jj < 4; ++jj) {
+              if (jj >= nhalf) break;
+              const int j = j0 + jj, c = j * 8;
+              float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+              if (c0 + c < p.Cin) {
+                if (sq0 >= 0) {
+                  va = *reinterpret_cast<const float4*>(row0 + c);
+                  vb = *reinterpret_cast<const float4*>(row0 + c + 4);
+                  if (pa0 | pb0 | (relu0 != 0)) {
+                    const float4 aa = pa0 ? *reinterpret_cast<const float4*>(ab0 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ab_ = pa0 ? *reinterpret_cast<const float4*>(ab0 + c + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ba = pb0 ? *reinterpret_cast<const float4*>(ab0 + CW + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 bb = pb0 ? *reinterpret_cast<const float4*>(ab0 + CW + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    va = pro4(va, aa, ba, relu0);
+                    vb = pro4(vb, ab_, bb, relu0);
+                  }
+                }
+                if (sq1 >= 0) {
+                  float4 ua = *reinterpret_cast<const float4*>(row1 + c), ub = *reinterpret_cast<const float4*>(row1 + c + 4);
+                  if (pa1 | pb1 | (relu1 != 0)) {
+                    const float4 aa = pa1 ? *reinterpret_cast<const float4*>(ab1 + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ab_ = pa1 ? *reinterpret_cast<const float4*>(ab1 + c + 4) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 ba = pb1 ? *reinterpret_cast<const float4*>(ab1 + CW + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 bb = pb1 ? *reinterpret_cast<const float4*>(ab1 + CW + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    ua = pro4(ua, aa, ba, relu1);
+                    ub = pro4(ub, ab_, bb, relu1);
+                  }
+                  va.x += ua.x; va.y += ua.y; va.z += ua.z; va.w += ua.w;
+                  vb.x += ub.x; vb.y += ub.y; vb.z += ub.z; vb.w += ub.w;
+                }
               }
-              if (sq1[u] >= 0) {
-                const float* row = rawf1 + sq1[u] * CW;
-                if (okA) x1a[u] = *reinterpret_cast<const float4*>(row + cA);
-                if (okB) x1b[u] = *reinterpret_cast<const float4*>(row + cB);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < WTU; ++u) {
-              if (q0 + u * 32 >= p.P) break;
-              const int q = q0 + u * 32 + pg;
-              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-              if (sq0[u] >= 0) {
-                if (okA) v0 = pro4(x0a[u], a0[0], b0[0], relu0);
-                if (okB) v1 = pro4(x0b[u], a1[0], b1[0], relu0);
-              }
-              if (sq1[u] >= 0) {
-                if (okA) { float4 t4 = pro4(x1a[u], a0[1], b0[1], relu1); v0.x += t4.x; v0.y += t4.y; v0.z += t4.z; v0.w += t4.w; }
-                if (okB) { float4 t4 = pro4(x1b[u], a1[1], b1[1], relu1); v1.x += t4.x; v1.y += t4.y; v1.z += t4.z; v1.w += t4.w; }
-              }
-              wg_store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, CW / 8, v0, v1, lane);
+              uint4 o;
+              o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
+              o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+              if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)j * (uint32_t)p.Ppad * 16u) = o;
             }
           }
         } else {
+          // dY sub-stage: 128 pixels x up to 64 channels, no prologue; warp -> (32 pixels, 4 chunks)
           const int cb = (tr.u - nA) * 64;
           const int c0 = co0 + cb;
-          const bool okA = c0 + cA < climit, okB = c0 + cB < climit;
           uint8_t* dst = sB + st * B_BYTES + (uint32_t)(cb / 8) * 129u * 16u;
-          const int nch = (p.BN - cb + 7) / 8;
+          const int nch = (p.BN - cb + 7) / 8;                   // chunks that exist in the B stage for this block
           const int* dyo = tab + p.tab_dy;
           const float* rawf = reinterpret_cast<const float*>(raw);
+          const int q = (warp >> 1) * 32 + lane;
+          const int j0 = (warp & 1) * 4;
+          const bool has = dyo[q] >= 0;
+          const float* row = rawf + q * 68;                       // dY raw pixel stride: 64 + 4 floats
 #pragma unroll
-          for (int it4 = 0; it4 < 4; ++it4) {
-            const int q = it4 * 32 + warp * 4 + pg;            // 128 pixels = 4 x (8 warps x 4)
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (dyo[q] >= 0) {
-              if (okA) v0 = *reinterpret_cast<const float4*>(rawf + q * 64 + cA);
-              if (okB) v1 = *reinterpret_cast<const float4*>(rawf + q * 64 + cB);
-            }
-            wg_store_chunks(dst, 129u, q, true, nch, v0, v1, lane);
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j0 + jj, c = j * 8;
+            if (j >= nch) break;
+            float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+            if (has && c0 + c < climit) { va = *reinterpret_cast<const float4*>(row + c); vb = *reinterpret_cast<const float4*>(row + c + 4); }
+            uint4 o;
+            o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
+            o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+            *reinterpret_cast<uint4*>(dst + (uint32_t)j * 129u * 16u + (uint32_t)q * 16u) = o;
           }
         }
         if (tr.u == nsub - 1) {
@@ -653,12 +662,12 @@ bool wg_plan(const hdn_conv* c, const WgGeom& gm, WgPlan& best) {
         if (c->src[s].uw == 2) pl.PWs[s] = pl.PW / 2 + 1;
       }
       pl.Ps[s] = s < c->nsrc ? pl.PHs[s] * pl.PWs[s] : 0;
-      pl.raw_off[s] = roff; roff += pl.Ps[s] * pl.CW * 4;
+      pl.raw_off[s] = roff; roff += pl.Ps[s] * (pl.CW + 4) * 4;
       pl.tab_src[s] = toff; toff += pl.Ps[s];
       pl.tab_vq[s] = toff; toff += s < c->nsrc ? pl.P : 0;
     }
     for (int s = 0; s < 2; ++s) { pl.ab_off[s] = roff; roff += s < c->nsrc ? 2 * pl.CW * 4 : 0; }
-    if (roff < 128 * 256) roff = 128 * 256;              // a dY sub-stage: 128 pixels x 64 channels
+    if (roff < 128 * 68 * 4) roff = 128 * 68 * 4;        // a dY sub-stage: 128 pixels x (64 + 4 pad) floats
     pl.raw_bytes = (roff + 127) / 128 * 128;
     pl.tab_dy = toff; toff += 128;
     pl.tab_ints = toff;

@@ -171,15 +171,20 @@ def profile_step(model, net, steps):
     for _ in range(steps):
         model.train_step_device(net)
     torch.cuda.synchronize()
-    agg = {}
-    for key, flops, s, e in be.prof:
+    agg, ops = {}, {}
+    for key, flops, s, e, name in be.prof:
         t = s.elapsed_time(e)
         a = agg.setdefault(key, [0.0, 0.0, 0])
         a[0] += t
         a[1] += flops
         a[2] += 1
+        if flops:
+            o = ops.setdefault((key, name), [0.0, 0.0, 0])
+            o[0] += t
+            o[1] += flops
+            o[2] += 1
     be.prof = None
-    return agg
+    return agg, ops
 
 
 def run_gpu(a):
@@ -250,20 +255,32 @@ def run_gpu(a):
 
     # roofline of the dominant kernel class, measured live with CUDA events (one extra instrumented step; every rank
     # takes part because the data-parallel exchange inside the step is collective)
-    agg = profile_step(m, net, a.profile_steps)
+    agg, ops = profile_step(m, net, a.profile_steps)
     if rank == 0:
         tot = sum(v[0] for v in agg.values())
-        top = max(agg.items(), key=lambda kv: kv[1][0])
-        k, (t, fl, n) = top
+        # the dominant kernel = the single most expensive convolution launch of the step (class + layer name)
+        (k, opname), (t, fl, n) = max(ops.items(), key=lambda kv: kv[1][0] / kv[1][2])
+        t, fl = t / n, fl / n                               # per launch
         sustained = peaks.get("bf16_tflops_sustained")
         peak_tf = sustained if sustained else 1400.0
         if "[simt]" in k:
             # fp32 FMA kernel: the bound that applies is the fp32 CUDA-core peak (148 SMs x 128 lanes x 2 x clock)
             peak_tf = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
         ach = fl / (t * 1e-3) / 1e12 if t > 0 else 0.0
-        line["roofline"] = {"kernel": k, "bound": "tensor" if "[tc]" in k else "fp32-fma", "achieved": ach,
+        traffic, tsrc = None, None
+        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tj):
+            with open(tj) as f:
+                tr = json.load(f)
+            what = k.split("[")[0].replace("conv_", "")
+            if opname in tr and what in tr[opname]:
+                traffic = tr[opname][what] * a.cols * a.batch
+                tsrc = tr["_source"]
+        line["roofline"] = {"kernel": "%s %s" % (k, opname), "bound": "tensor" if "[tc]" in k else "fp32-fma", "achieved": ach,
                             "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-                            "traffic": None, "share_of_step": t / tot if tot else None, "launches": n,
+                            "traffic": traffic, "traffic_source": tsrc, "ms_per_launch": t,
+                            "share_of_step": t * n / tot if tot else None, "launches": n,
+                            "flop_per_launch": fl,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "[tc]" in k and sustained
                             else ("fallback 1.4 PF" if "[tc]" in k else "fp32 FMA nominal at max SM clock")}
         line["kernel_classes"] = {kk: {"ms": round(v[0] / a.profile_steps, 3), "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 2),

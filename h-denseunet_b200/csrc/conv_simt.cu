@@ -306,6 +306,36 @@ __global__ void __launch_bounds__(NT) conv_wgrad_simt(const hdn_conv c, float* _
   }
 }
 
+// wgrad of a 1x1x1 convolution with very few output channels (the 3-class classifiers, hybridnet.py:260,419):
+// HBM-bound column reduction dw[ci][co] += sum_pos A[pos][ci] * dY[pos][co]; thread = (input channel, position lane).
+__global__ void __launch_bounds__(256) conv_wgrad_small_n(const hdn_conv c, float* __restrict__ dw, const int64_t M,
+                                                          const int lanes) {
+  __shared__ float red[256 * 4];
+  const hdn_src& s = c.src[0];
+  const int ci = threadIdx.x % c.Cin, pl = threadIdx.x / c.Cin;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    const float a = s.pa ? __ldg(s.pa + ci) : 1.f, b = s.pb ? __ldg(s.pb + ci) : 0.f;
+    for (int64_t m = (int64_t)blockIdx.x * lanes + pl; m < M; m += (int64_t)gridDim.x * lanes) {
+      float x = fmaf(a, __ldg(s.t.p + m * s.t.ldc + s.t.coff + ci), b);
+      if (s.relu) x = fmaxf(x, 0.f);
+      const float* dy = c.y.p + m * c.y.ldc + c.y.coff;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < c.Cout) acc[j] = fmaf(x, __ldg(dy + j), acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.x * 4 + j] = acc[j];
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] += red[(l * c.Cin + ci) * 4 + j];
+    for (int j = 0; j < c.Cout; ++j) atomicAdd(dw + (int64_t)ci * c.Cout + j, acc[j]);
+  }
+}
+
 // out[c] += sum_m y[m][c]   (bias gradient)
 __global__ void __launch_bounds__(256) colsum_kernel(hdn_tensor y, int64_t M, int C, float* out,
                                                      int64_t rows_per_block) {
@@ -415,6 +445,15 @@ int hdn_colsum(hdn_tensor y, int64_t M, int C, float* out, cudaStream_t st) {
 
 int hdn_conv_wgrad_simt(const hdn_conv* c, float* dw, cudaStream_t st) {
   const int64_t M = (int64_t)c->N * c->D * c->H * c->W;
+  if (c->kd * c->kh * c->kw == 1 && c->Cout <= 4 && c->Cin <= 256 && c->nsrc == 1 && c->src[0].ud == 1 && c->src[0].uh == 1 &&
+      c->src[0].uw == 1 && c->sd == 1 && c->sh == 1 && c->sw == 1) {
+    const int lanes = 256 / c->Cin;
+    int64_t blocks = hdn_cdiv(M, (int64_t)lanes * 64);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    conv_wgrad_small_n<<<(unsigned)blocks, 256, 0, st>>>(*c, dw, M, lanes);
+    HDN_CHECK_LAUNCH("conv_wgrad_small_n");
+    return HDN_OK;
+  }
   const int taps = c->kd * c->kh * c->kw;
   const int64_t tiles = hdn_cdiv(c->Cin, BM) * hdn_cdiv(c->Cout, BN);
   // aim for ~8 waves of 148 SMs, at least 256 rows per split

@@ -121,7 +121,8 @@ class CudaBackend(object):
     def __init__(self):
         self.lib = _lib.load()
         self.launches = 0
-        self.prof = None          # list of (key, flops, start_event, end_event) while profiling
+        self.prof = None          # list of (key, flops, start_event, end_event, op name) while profiling
+        self._cur = ""
 
     def _run(self, key, flops, n_launch, fn, *args):
         """Issue one C-ABI call; with profiling on, bracket it with CUDA events on the launch stream."""
@@ -132,7 +133,7 @@ class CudaBackend(object):
         s.record()
         rc = fn(*args)
         e.record()
-        self.prof.append((key, flops, s, e))
+        self.prof.append((key, flops, s, e, self._cur))
         return rc
 
     @staticmethod
@@ -207,6 +208,7 @@ class CudaBackend(object):
         return int(self.lib.hdn_conv_tc_workspace(C.byref(self._conv(d)), which))
 
     def conv_fprop(self, d):
+        self._cur = d.name
         _lib.check(self._run(self._conv_key(d, "fprop"), self._conv_flops(d), 1, self.lib.hdn_conv_fprop,
                              C.byref(self._conv(d)), self.stream), "hdn_conv_fprop " + d.name)
 
@@ -218,10 +220,12 @@ class CudaBackend(object):
                 arr[i] = self._epi(e, d.Cin)
             d.__dict__["_c_epis"] = arr
         nact = sum(1 for e in epis if e.mode != 2)
+        self._cur = d.name
         _lib.check(self._run(self._conv_key(d, "dgrad"), self._conv_flops(d) * nact, nact, self.lib.hdn_conv_dgrad,
                              C.byref(self._conv(d, True)), arr, self.stream), "hdn_conv_dgrad " + d.name)
 
     def conv_wgrad(self, d, dw, dbias):
+        self._cur = d.name
         _lib.check(self._run(self._conv_key(d, "wgrad"), self._conv_flops(d), 1 + (dbias is not None),
                              self.lib.hdn_conv_wgrad, C.byref(self._conv(d, True)), dw.data_ptr(), _ptr(dbias),
                              self.stream), "hdn_conv_wgrad " + d.name)

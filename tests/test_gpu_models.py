@@ -196,3 +196,36 @@ def test_sliding_window_matches_oracle(cuda_dev):
     o1, o2 = orc.predict_tumor_inwindow(pred, vol, 3, mini, maxi, 32, 8)
     assert np.abs(s1 - o1).max() < 2e-3 and np.abs(s2 - o2).max() < 2e-3
     assert rel_l2(s1, o1) < 1e-3
+
+
+def test_hybrid_train_step_bf16_tensor_cores(cuda_dev):
+    """precision="bf16": all 231 convolutions on the tcgen05 path (operands rounded to bf16, fp32 accumulation).
+    Bounds: logits within 5e-2 rel-L2 of the fp32 oracle after 161 + 53 layers of bf16 operand rounding (measured
+    ~1.5e-2), loss within 1e-2, every large parameter gradient within 0.25 rel-L2 / cosine > 0.97 of the fp64 oracle
+    (measured ~3e-2 typical).  The 1e-3 north-star bound is the fp32 path's (test_hybrid_train_step_fp32)."""
+    a = Args(b=1, input_size=64, input_cols=8)
+    m = hdn.dense_rnn_net(a, precision="bf16")
+    m.dropout = False
+    perturb_params(m)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+    vol, lab = synthetic_slab(1, 64, 8)
+    w0 = m.get_weights_dict()
+    ctx, logits = orc.forward_hybrid(w0, vol, training=True, variant="end2end", requires_grad=True, dtype=torch.float64)
+    loss = orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), logits, crop=True)
+    og = orc.grads_of(ctx, loss)
+    got_loss = m.train_on_batch(vol, lab)
+    net = m.nets[True]
+    assert all(any(p) for _, p in net.report), "a convolution fell back to the fp32 FMA path"
+    assert sum(1 for _, p in net.report if all(p)) >= len(net.report) - 2       # only the 3-class classifiers' dgrad/wgrad stay fp32
+    assert rel_l2(m._logits_to_host(net), logits.detach().numpy()) < 5e-2
+    assert abs(got_loss - float(loss.detach())) <= 1e-2 * abs(float(loss.detach()))
+    eg = m.get_grads_dict()
+    bad = []
+    for k, g in og.items():
+        if g is None or np.abs(g).max() < 1e-6 or not k.endswith("kernel"):
+            continue
+        e = rel_l2(eg[k], g)
+        cos = float((eg[k].ravel() * g.ravel()).sum() / (np.linalg.norm(eg[k]) * np.linalg.norm(g) + 1e-30))
+        if e > 0.25 or cos < 0.97:
+            bad.append((k, e, cos))
+    assert not bad, bad[:8]

@@ -46,7 +46,7 @@ constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs < N
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
 constexpr int RB = 32;        // dgrad epilogue: rows fetched ahead per lane
-constexpr int MAXC0 = 12;     // copies per producer thread and stage, source 0 (180 px x 16 quads / 256 threads)
+constexpr int MAXC0 = 14;     // copies per producer thread and stage, source 0 (4-tap stems' dgrad: 19x11 px x 16 quads / 256 threads)
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 constexpr int TU = 3;         // transform: pixel groups looked up / fetched ahead per warp
 
@@ -1049,6 +1049,8 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   const TcGeom g = tc_geom(c, mode);
   const TcPlan pl = tc_plan(c, g, mode);
   HDN_CHECK_ARG(g.s2d || pl.nraw >= 2, "conv tc: shared memory cannot hold two raw stages (BN=%d)", pl.BN);
+  HDN_CHECK_ARG(g.s2d || (pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD),
+                "conv tc: patch of %d / %d pixels exceeds the per-thread copy list", pl.Ps[0], pl.Ps[1]);
   HDN_CHECK_ARG(c->ws != nullptr && c->ws_bytes >= pl.ws_elems * 2, "conv tc: workspace too small (%lld < %lld bytes)",
                 (long long)c->ws_bytes, (long long)pl.ws_elems * 2);
   static bool attr_set = false;

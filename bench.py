@@ -120,7 +120,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, a.cpu_threads)
     size, cols = a.cpu_size, a.cpu_cols
     fn, sample = cpu_step_fn(size, cols, threads)
     warm, _ = cpu_step_fn(32, 8, threads)                   # untimed warm-up on a tiny slab
@@ -289,7 +289,7 @@ def run_gpu(a):
                                   for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
         # CPU baseline on this box's host cores, bounded sample
         if not a.no_cpu:
-            threads = os.cpu_count() or 1
+            threads = min(os.cpu_count() or 1, a.cpu_threads)   # oneDNN convolutions of this size stop scaling past ~32 threads
             fn, sample = cpu_step_fn(a.cpu_size, a.cpu_cols, threads)
             warm, _ = cpu_step_fn(32, 8, threads)           # thread pools / allocator warm-up on a tiny slab, untimed
             warm()
@@ -323,6 +323,7 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=1)
     ap.add_argument("--cpu-size", type=int, default=160)
     ap.add_argument("--cpu-cols", type=int, default=8)
+    ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU arm (capped at the core count)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -241,7 +241,7 @@ def run_gpu(a):
     line = {
         "metric": METRIC, "value": value, "unit": "slabs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if a.precision == "bf16" and ntc else "f32", "data": "synthetic",
+        "dtype": "bf16" if a.precision in ("bf16", "bf16x3") and ntc else "f32", "data": "synthetic",
         "config": {"workload": "H-DenseUNet end2end train step (hybridnet.dense_rnn_net): %d slab(s)/GPU of %dx%dx%d, "
                                "fwd + weighted CE + bwd + Nesterov SGD%s" % (
                                    a.batch, a.size, a.size, a.cols, " + P2P grad reduce" if world > 1 else ""),
@@ -277,13 +277,13 @@ def run_gpu(a):
             if opname in tr and what in tr[opname]:
                 traffic = tr[opname][what] * a.cols * a.batch
                 tsrc = tr["_source"]
-        line["roofline"] = {"kernel": "%s %s" % (k, opname), "bound": "tensor" if "[tc]" in k else "fp32-fma", "achieved": ach,
+        line["roofline"] = {"kernel": "%s %s" % (k, opname), "bound": "tensor" if "[tc" in k else "fp32-fma", "achieved": ach,
                             "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
                             "traffic": traffic, "traffic_source": tsrc, "ms_per_launch": t,
                             "share_of_step": t * n / tot if tot else None, "launches": n,
                             "flop_per_launch": fl,
-                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "[tc]" in k and sustained
-                            else ("fallback 1.4 PF" if "[tc]" in k else "fp32 FMA nominal at max SM clock")}
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "[tc" in k and sustained
+                            else ("fallback 1.4 PF" if "[tc" in k else "fp32 FMA nominal at max SM clock")}
         line["kernel_classes"] = {kk: {"ms": round(v[0] / a.profile_steps, 3), "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 2),
                                         "launches": v[2] // a.profile_steps}
                                   for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
@@ -317,7 +317,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cols", type=int, default=48)
     ap.add_argument("--batch", type=int, default=2, help="slabs per GPU (north star: 2)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"],
+                    help="bf16: tcgen05, operands rounded to bf16; bf16x3: tcgen05, operands split into bf16 head + tail "
+                         "(3 MMAs per step, fp32-grade results); fp32: FMA parity path")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=1)

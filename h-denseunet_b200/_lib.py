@@ -88,7 +88,7 @@ class BnGrad(C.Structure):
 
 EXPORTS = [
     "hdn_last_error", "hdn_version", "hdn_conv_fprop", "hdn_conv_dgrad", "hdn_conv_wgrad",
-    "hdn_conv_tc_supported", "hdn_conv_tc_workspace", "hdn_pool_fwd", "hdn_pool_bwd", "hdn_bn_fold", "hdn_bn_param_grad",
+    "hdn_conv_tc_supported", "hdn_conv_tc_workspace", "hdn_conv_tc_plan", "hdn_pool_fwd", "hdn_pool_bwd", "hdn_bn_fold", "hdn_bn_param_grad",
     "hdn_bn_bwd_apply", "hdn_dropout_bwd", "hdn_col_stats", "hdn_wce_accum", "hdn_wce_grad",
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
     "hdn_window_accumulate", "hdn_window_finalize", "hdn_dev_malloc", "hdn_dev_free",
@@ -118,6 +118,7 @@ def load():
         "hdn_conv_dgrad": [C.POINTER(Conv), C.POINTER(DgradEpi), vp],
         "hdn_conv_wgrad": [C.POINTER(Conv), vp, vp, vp],
         "hdn_conv_tc_supported": [C.POINTER(Conv), i32],
+        "hdn_conv_tc_plan": [C.POINTER(Conv), i32, C.POINTER(C.c_int32)],
         "hdn_pool_fwd": [C.POINTER(Pool), vp],
         "hdn_pool_bwd": [C.POINTER(Pool), C.POINTER(DgradEpi), vp],
         "hdn_bn_fold": [C.POINTER(BnFold), vp],

@@ -38,10 +38,20 @@ extern "C" int64_t hdn_conv_tc_workspace(const hdn_conv* c, int pass) {
   return (int64_t)hdn_tc_workspace_bytes(c, pass);
 }
 
+int hdn_tc_plan_info(const hdn_conv* c, int pass, int* out);
+int hdn_wgrad_plan_info(const hdn_conv* c, int* out);
+extern "C" int hdn_conv_tc_plan(const hdn_conv* c, int pass, int32_t* out16) {
+  int rc = hdn_validate_conv(c);
+  if (rc) return rc;
+  HDN_CHECK_ARG(out16 != nullptr && pass >= 0 && pass <= 2, "conv_tc_plan: bad arguments");
+  if (!hdn_tc_supported(c, pass)) { hdn_set_error("conv_tc_plan: tcgen05 path does not take this shape"); return HDN_ERR_UNSUPPORTED; }
+  return pass == 2 ? hdn_wgrad_plan_info(c, out16) : hdn_tc_plan_info(c, pass, out16);
+}
+
 extern "C" int hdn_conv_fprop(const hdn_conv* c, void* stream) {
   int rc = hdn_validate_conv(c);
   if (rc) return rc;
-  if (c->precision == 1) {
+  if (c->precision == 1 || c->precision == 2) {
     if (!hdn_tc_supported(c, 0)) { hdn_set_error("conv_fprop: tcgen05 path does not take this shape"); return HDN_ERR_UNSUPPORTED; }
     return hdn_conv_fprop_tc(c, (cudaStream_t)stream);
   }
@@ -59,7 +69,7 @@ extern "C" int hdn_conv_dgrad(const hdn_conv* c, const hdn_dgrad_epi* epi, void*
                   "conv_dgrad: epilogue %d has no destination", i);
     HDN_CHECK_ARG((epi[i].s1 == nullptr) == (epi[i].s2 == nullptr), "conv_dgrad: s1/s2 must both be set or both NULL");
   }
-  if (c->precision == 1) {
+  if (c->precision == 1 || c->precision == 2) {
     if (!hdn_tc_supported(c, 1)) { hdn_set_error("conv_dgrad: tcgen05 path does not take this shape"); return HDN_ERR_UNSUPPORTED; }
     return hdn_conv_dgrad_tc(c, epi, (cudaStream_t)stream);
   }
@@ -74,7 +84,7 @@ extern "C" int hdn_conv_wgrad(const hdn_conv* c, float* dw, float* dbias, void* 
     rc = hdn_colsum(c->y, (int64_t)c->N * c->D * c->H * c->W, c->Cout, dbias, (cudaStream_t)stream);
     if (rc) return rc;
   }
-  if (c->precision == 1) {
+  if (c->precision == 1 || c->precision == 2) {
     if (!hdn_tc_supported(c, 2)) { hdn_set_error("conv_wgrad: tcgen05 path does not take this shape"); return HDN_ERR_UNSUPPORTED; }
     return hdn_conv_wgrad_tc(c, dw, (cudaStream_t)stream);
   }

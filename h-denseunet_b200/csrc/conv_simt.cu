@@ -412,6 +412,7 @@ int hdn_validate_conv(const hdn_conv* c) {
                 "conv: output grid larger than the geometry allows");
   HDN_CHECK_ARG(c->y.ldc >= c->y.coff + c->Cout, "conv: y channel window exceeds ldc");
   HDN_CHECK_ARG(c->drop_keep > 0.f && c->drop_keep <= 1.f, "conv: drop_keep must be in (0,1]");
+  HDN_CHECK_ARG(c->precision >= 0 && c->precision <= 2, "conv: precision must be 0 (fp32), 1 (bf16) or 2 (bf16x3), got %d", c->precision);
   return HDN_OK;
 }
 

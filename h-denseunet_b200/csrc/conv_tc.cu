@@ -1,5 +1,8 @@
 // tcgen05 implicit-GEMM convolution path (precision == 1): bf16 operands, fp32 accumulation in
-// tensor memory.  Covers the stride-1 "same" convolutions of the dense blocks, transitions and
+// tensor memory.  precision == 2 ("bf16x3") is the same kernel with both operands split into a bf16
+// head and a bf16 tail (x = hi + lo, lo = bf16(x - hi)) and three MMAs per K step,
+// hi*hi + lo*hi + hi*lo, i.e. ~16 significant bits per operand: fp32-grade results (the 1e-3 parity
+// bound) from the bf16 tensor pipe.  Covers the stride-1 "same" convolutions of the dense blocks, transitions and
 // decoders: kernels 1x1x1, 1x3x3, 3x3x3 (hybridnet.py:264-298, 11-45, 235-260, 146-176) and the
 // stride-2 7x7(x7) stems in space-to-depth form, in fprop and dgrad; everything the reference
 // puts around them (BN -> Scale -> ReLU, ZeroPadding, UpSampling, Add, bias, dropout, batch
@@ -67,6 +70,7 @@ struct TcParams {
   hdn_src src[2];             // A operand sources
   const __nv_bfloat16* wpack;
   int mode;                   // 0 fprop, 1 dgrad
+  int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
   int pd_lo, ph_lo, pw_lo;    // patch origin = tile origin - p*_lo (padding in front of tap 0)
   int s2d;                    // 1: A operand is the space-to-depth view of a stride-2 convolution's input:
                               //    s2d pixel (d,h,w) holds channels (rd,rh,rw,c) = x[2d+rd][2h+rh][2w+rw][c], ldc == 4
@@ -201,7 +205,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t A_BYTES = 8u * p.Ppad * 16u;
-  const uint32_t B_BYTES = (uint32_t)p.BN * (uint32_t)p.CK * 2u;
+  const uint32_t B_HALF = (uint32_t)p.BN * (uint32_t)p.CK * 2u;          // one bf16 weight block
+  const uint32_t B_BYTES = p.split ? 2u * B_HALF : B_HALF;                 // bf16x3: head block | tail block
   uint8_t* sA = smem;
   uint8_t* sB = sA + NSA * A_BYTES;
   uint8_t* sRaw = sB + p.nsb * B_BYTES;
@@ -430,8 +435,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
               }
               uint4 o;
-              o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
-              o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+              if (!p.split) {
+                o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
+                o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+              } else {                                             // head -> chunk j, tail -> chunk nch + j
+                uint4 t;
+                tc::pack_split_bf16x2(va.x, va.y, o.x, t.x); tc::pack_split_bf16x2(va.z, va.w, o.y, t.y);
+                tc::pack_split_bf16x2(vb.x, vb.y, o.z, t.z); tc::pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+                if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)(nch + j) * (uint32_t)p.Ppad * 16u) = t;
+              }
               if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)j * (uint32_t)p.Ppad * 16u) = o;
             }
           }
@@ -481,7 +493,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int u = 0; u < UB; ++u) {
             if (q0 + u * 32 >= p.P) break;                  // warp-uniform
             const int q = q0 + u * 32 + pg;
-            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, r0[u], make_float4(0.f, 0.f, 0.f, 0.f), lane);
+            float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.split) {                                  // quad B slot (chunks 4-7) carries the tail of quad A's channels
+              const float4 x = r0[u];
+              r1.x = x.x - __bfloat162float(__float2bfloat16_rn(x.x)); r1.y = x.y - __bfloat162float(__float2bfloat16_rn(x.y));
+              r1.z = x.z - __bfloat162float(__float2bfloat16_rn(x.z)); r1.w = x.w - __bfloat162float(__float2bfloat16_rn(x.w));
+            }
+            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, r0[u], r1, lane);
           }
         }
         tc::fence_proxy_async_smem();
@@ -497,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       it_init(p, it);
       int sb = 0;
       uint32_t phb = 0;
-      const size_t blk = (size_t)p.BN * p.CK;
+      const size_t blk = (size_t)p.BN * p.CK * (p.split ? 2 : 1);
       while (!it.done) {
         const __nv_bfloat16* src = p.wpack + (((size_t)it.t.n_tile * p.KB + it.kb) * T + (size_t)it.dz * taps_hw) * blk;
         for (int t2 = 0; t2 < taps_hw; ++t2, src += blk) {
@@ -523,6 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t acc = 0, tmem_d = tmem_base;
       const uint64_t adesc_hi = tc::make_smem_desc(0, lbo_a, sbo_a), bdesc_hi = tc::make_smem_desc(0, lbo_b, sbo_b);
       const uint64_t kstep_a = (uint64_t)((2u * lbo_a) >> 4), kstep_b = (uint64_t)((2u * lbo_b) >> 4);
+      const uint64_t tail_a = (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_a) >> 4), tail_b = (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_b) >> 4);
       TT_DECL(t_acc); TT_DECL(t_afull); TT_DECL(t_bfull); TT_DECL(t_mma); TT_DECL(n_st);
       while (!it.done) {
         TT_BEGIN;
@@ -552,10 +571,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           TT_ADD(t_bfull);
           const uint64_t ad = a_desc0 + tap_units;
           const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
-          tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
-          if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
-          if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
-          if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
+          if (!p.split) {
+            tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
+            if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
+            if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
+            if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
+          } else {
+            // bf16x3: tails first (small terms), head x head last; tail operands sit CK/8 chunks behind the heads
+            for (int s = 0; s < nk; ++s) {
+              const uint64_t ah = ad + (uint64_t)s * kstep_a, bh = bd + (uint64_t)s * kstep_b;
+              tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc, acc);
+              tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc, 1u);
+              tc::umma_bf16(tmem_d, ah, bh, idesc, 1u);
+              acc = 1;
+            }
+          }
           acc = 1;
           tc::umma_commit(&b_empty[sb]);
           if (++sb == p.nsb) { sb = 0; phb ^= 1; }
@@ -827,12 +857,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------- weight packing
-// out[n_tile][kb][tap][chunk j < KC/8][n][8]  (bf16)  =  B[n = column][k = kb*KC + j*8 + e]
+// out[n_tile][kb][tap][part < nsplit][chunk j < KC/8][n][8]  (bf16)  =  B[n = column][k = kb*KC + j*8 + e]
+//   part 0 = bf16(B), part 1 (bf16x3 only) = bf16(B - part 0)
 //   role 0 (fprop): B[n][k] = w[tap][k][n]                       K = Cin,  NC = Cout
 //   role 1 (dgrad): B[n][k] = w[flip(tap)][n][k]                 K = Cout, NC = Cin
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int Cin, int Cout, int kd, int kh, int kw, int BN, int KB,
-                                                           int KC, int role, long long total16) {
+                                                           int KC, int role, int nsplit, long long total16) {
   // one thread per 16-byte output unit (n, chunk j): 8 consecutive k.  role 0 reads w[tap][k][col] (threads
   // adjacent in n -> coalesced over col); role 1 reads w[tap'][col][k..k+8) (two float4 per thread).
   const int T = kd * kh * kw;
@@ -842,6 +873,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     const int n = (int)(t % BN); t /= BN;
     const int nj = KC / 8;
     const int j = (int)(t % nj); t /= nj;
+    const int part = (int)(t % nsplit); t /= nsplit;
     const int tap = (int)(t % T); t /= T;
     const int kb = (int)(t % KB); t /= KB;
     const int nt = (int)t;
@@ -859,6 +891,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
         for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e);
       }
     }
+    if (part) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16_rn(v[e]));
+    }
     uint4 o;
     o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
     o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
@@ -871,8 +907,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 //   role 0 (fprop): B[n = co][k = (rd,rh,rw,c)] = w[t(tq,r)][c][co]
 //   role 1 (dgrad): B[n = (rd,rh,rw,c)][k = co] = w[t(3 - tq', r)][c][co]   (taps flipped)
 __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
-                                                               int Cin, int Cout, int three_d, int BN, int KB, int role,
-                                                               long long total16) {
+                                                               int Cin, int Cout, int three_d, int BN, int KB, int KC,
+                                                               int role, int nsplit, long long total16) {
   const int TD = three_d ? 4 : 1, T = TD * 16;
   const int quads = three_d ? 8 : 4;
   const int K = role == 0 ? quads * 4 : Cout, NC = role == 0 ? Cout : quads * 4;
@@ -880,7 +916,9 @@ __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __re
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total16; idx += (long long)gridDim.x * 256) {
     long long t = idx;
     const int n = (int)(t % BN); t /= BN;
-    const int j = (int)(t % 8); t /= 8;
+    const int nj = KC / 8;
+    const int j = (int)(t % nj); t /= nj;
+    const int part = (int)(t % nsplit); t /= nsplit;
     int tap = (int)(t % T); t /= T;
     const int kb = (int)(t % KB); t /= KB;
     const int nt = (int)t;
@@ -889,7 +927,7 @@ __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __re
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = kb * 64 + j * 8 + e, col = nt * BN + n;
+      const int k = kb * KC + j * 8 + e, col = nt * BN + n;
       v[e] = 0.f;
       if (k < K && col < NC) {
         const int sc = role == 0 ? k : col, co = role == 0 ? col : k;    // s2d channel (rd,rh,rw,c), output channel
@@ -898,6 +936,7 @@ __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __re
         if (c < Cin && tw >= 0 && th >= 0 && td >= 0 && tw < 7 && th < 7 && td < k7d)
           v[e] = __ldg(w + ((((long long)td * 7 + th) * 7 + tw) * Cin + c) * Cout + co);
       }
+      if (part) v[e] -= __bfloat162float(__float2bfloat16_rn(v[e]));
     }
     uint4 o;
     o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
@@ -986,11 +1025,12 @@ TcGeom tc_geom(const hdn_conv* c, int mode) {
 TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   TcPlan pl;
   memset(&pl, 0, sizeof(pl));
+  const int nsplit = c->precision == 2 ? 2 : 1;           // bf16x3: head + tail of every operand
   pl.n_tiles = (g.NC + 255) / 256 + extra_tiles;
   int bn = (g.NC + pl.n_tiles - 1) / pl.n_tiles;
   pl.BN = (bn + 15) / 16 * 16;
   const int nsrc = mode == 0 ? c->nsrc : 1;               // dgrad: the A operand is dY alone
-  pl.CK = (nsrc == 2) ? 32 : 64;                          // channels per stage (two raw patches must fit a stage)
+  pl.CK = (nsrc == 2 || nsplit == 2) ? 32 : 64;           // channels per stage (two raw patches, or head + tail chunks, must fit a stage)
   pl.KB = (g.K + pl.CK - 1) / pl.CK;
   pl.flat = g.flat;
   pl.PH = 16 + g.kh - 1;
@@ -1015,11 +1055,11 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   for (int s = 0; s < 2; ++s) { pl.ab_off[s] = off; off += s < nsrc ? 2 * pl.CK * 4 : 0; }
   pl.raw_bytes = (off + 127) / 128 * 128;
   pl.tab_ints = toff;
-  const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * pl.CK * 2;
+  const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * pl.CK * 2 * nsplit;
   int cols = 32;
   while (cols < 2 * pl.BN) cols *= 2;                      // two accumulator buffers
   pl.tmem_cols = cols;
-  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * pl.CK;
+  pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * pl.CK * nsplit;
   const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES +
                       (2 * NSA + 2 * NSB_MAX + 4) * 8 + 16;
   const long long budget = 226 * 1024;
@@ -1048,6 +1088,7 @@ TcPlan tc_plan(const hdn_conv* c, const TcGeom& g, int mode) {
 int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_t st) {
   const TcGeom g = tc_geom(c, mode);
   const TcPlan pl = tc_plan(c, g, mode);
+  const int nsplit = c->precision == 2 ? 2 : 1;
   HDN_CHECK_ARG(g.s2d || pl.nraw >= 2, "conv tc: shared memory cannot hold two raw stages (BN=%d)", pl.BN);
   HDN_CHECK_ARG(g.s2d || (pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD),
                 "conv tc: patch of %d / %d pixels exceeds the per-thread copy list", pl.Ps[0], pl.Ps[1]);
@@ -1064,9 +1105,9 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     long long total = pl.ws_elems / 8;
     unsigned gr = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     if (g.s2d || g.scatter)
-      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, mode, total);
+      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, total);
     else
-      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, total);
+      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, total);
     HDN_CHECK_LAUNCH("pack_weights");
   }
   TcParams p;
@@ -1087,6 +1128,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.M = (long long)c->N * c->D * c->H * c->W;
   p.wpack = wp;
   p.mode = mode;
+  p.split = nsplit == 2 ? 1 : 0;
   if (mode == 0) {
     p.nsrc = c->nsrc;
     p.src[0] = c->src[0];
@@ -1160,6 +1202,20 @@ int hdn_tc_supported(const hdn_conv* c, int pass) {
 long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
   if (!hdn_tc_supported(c, pass) || pass == 2) return 0;
   return tc_plan(c, tc_geom(c, pass), pass).ws_elems * 2;
+}
+
+// launch plan of the fprop / dgrad kernel for this descriptor (host arithmetic only; see hdn_conv_tc_plan in hdn.h)
+int hdn_tc_plan_info(const hdn_conv* c, int pass, int* out) {
+  const TcGeom g = tc_geom(c, pass);
+  const TcPlan pl = tc_plan(c, g, pass);
+  const long long M = (long long)c->N * c->D * c->H * c->W;
+  const long long tiles = pl.flat ? (M + 127) / 128 : (long long)c->N * c->D * pl.tiles_h * pl.tiles_w;
+  out[0] = pl.BN; out[1] = pl.n_tiles; out[2] = pl.KB; out[3] = pl.CK; out[4] = pl.nsb; out[5] = pl.nraw;
+  out[6] = pl.tmem_cols; out[7] = (int)pl.smem; out[8] = pl.flat; out[9] = pl.P; out[10] = c->precision == 2 ? 1 : 0;
+  out[11] = g.s2d; out[12] = (tiles * pl.n_tiles < (1ll << 31)) ? (int)(tiles * pl.n_tiles) : -1;
+  out[13] = pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD;   // per-thread copy list holds the patch
+  out[14] = g.K; out[15] = g.NC;
+  return HDN_OK;
 }
 
 int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st) { return tc_launch(c, nullptr, 0, st); }

@@ -13,6 +13,11 @@
 //
 //   warps 0-7  producers (patch + dY tile -> bf16 chunks in shared memory), then epilogue
 //   warp  8    MMA issuer (one elected thread)
+//
+// precision == 2 ("bf16x3"): the same MMA stream on a folded tile.  A CTA owns 64 input channels whose bf16
+// heads fill GEMM rows 0-63 and whose tails (x - head) fill rows 64-127; the dY tile carries BN head columns
+// followed by BN tail columns (N = 2*BN).  One M=128 x N=2BN MMA then forms all four head/tail products and
+// the epilogue reduces the four quadrants into the same dW entries with the vector reductions it already uses.
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
@@ -30,6 +35,7 @@ struct WgParams {
   int kd, kh, kw;
   int Cin, Cout;
   int BN, G, groups;           // column tile, taps per group, number of tap groups
+  int split, BNe, CI;          // bf16x3 folding: BNe = GEMM N (2*BN when split), CI = input channels per CTA (64 when split, else 128)
   int ci_tiles, co_tiles;
   int flat;
   int PH, PW, P, Ppad;         // patch of ONE tap group (rows PH, cols PW)
@@ -63,7 +69,7 @@ __device__ __forceinline__ float4 pro4(float4 x, float4 a, float4 b, int relu) {
 // ppad*16 bytes).  offs[s*npx + q] is the element offset of pixel q in source s (or -1 => zeros).
 __device__ __forceinline__ void stage_block(const hdn_src* src, int nsrc, const float* const* base, const int* offs,
                                             int npx, int ppad, int cbase, int climit, uint8_t* dst, int nchunks,
-                                            int pwarp, int lane, int s2d_quads = 0) {
+                                            int pwarp, int lane, int s2d_quads = 0, uint8_t* dst_lo = nullptr) {
   const int l8 = lane & 7, pg = lane >> 3;
   const bool even = (l8 & 1) == 0;
   const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
@@ -114,14 +120,28 @@ __device__ __forceinline__ void stage_block(const hdn_src* src, int nsrc, const 
           if (okB) { float4 t = pro4(r1[u][s], a1[s], b1[s], relu); v1.x += t.x; v1.y += t.y; v1.z += t.z; v1.w += t.w; }
         }
       }
-      const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
-      const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+      uint32_t p00, p01, p10, p11, t00 = 0, t01 = 0, t10 = 0, t11 = 0;
+      if (dst_lo) {
+        tc::pack_split_bf16x2(v0.x, v0.y, p00, t00); tc::pack_split_bf16x2(v0.z, v0.w, p01, t01);
+        tc::pack_split_bf16x2(v1.x, v1.y, p10, t10); tc::pack_split_bf16x2(v1.z, v1.w, p11, t11);
+      } else {
+        p00 = tc::pack_bf16x2(v0.x, v0.y); p01 = tc::pack_bf16x2(v0.z, v0.w);
+        p10 = tc::pack_bf16x2(v1.x, v1.y); p11 = tc::pack_bf16x2(v1.z, v1.w);
+      }
       const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
       const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
       uint4 o;
       if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }
       else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }
       if (q < npx && chunk < nchunks) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
+      if (dst_lo) {                                          // warp-uniform: the tails, regrouped the same way
+        const uint32_t u0 = even ? t10 : t00, u1 = even ? t11 : t01;
+        const uint32_t y0 = __shfl_xor_sync(0xffffffffu, u0, 1), y1 = __shfl_xor_sync(0xffffffffu, u1, 1);
+        uint4 ot;
+        if (even) { ot.x = t00; ot.y = t01; ot.z = y0; ot.w = y1; }
+        else      { ot.x = y0; ot.y = y1; ot.z = t10; ot.w = t11; }
+        if (q < npx && chunk < nchunks) *reinterpret_cast<uint4*>(dst_lo + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = ot;
+      }
     }
   }
 }
@@ -129,27 +149,13 @@ __device__ __forceinline__ void stage_block(const hdn_src* src, int nsrc, const 
 __device__ __forceinline__ void wg_cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void wg_store_chunks(uint8_t* dst, uint32_t ppad, int q, bool qok, int nchunks, float4 v0, float4 v1, int lane) {
-  const int l8 = lane & 7;
-  const bool even = (l8 & 1) == 0;
-  const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
-  const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
-  const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
-  const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
-  const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-  uint4 o;
-  if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }
-  else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }
-  if (qok && chunk < nchunks) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
-}
 constexpr int NTW = 3;         // geometry-table buffers
-constexpr int WTU = 3;         // transform: pixel groups fetched ahead per warp
 
 __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t A_BYTES = 16u * p.Ppad * 16u;                       // 128 channels of the patch
-  const uint32_t B_BYTES = (uint32_t)((p.BN + 7) / 8) * 129u * 16u;  // dY tile, BN channels x 128 pixels
+  const uint32_t B_BYTES = (uint32_t)((p.BNe + 7) / 8) * 129u * 16u; // dY tile, BNe columns x 128 pixels
   uint8_t* sA = smem;
   uint8_t* sB = sA + NS * A_BYTES;
   int* offs = reinterpret_cast<int*>(sB + NS * B_BYTES);             // [NS][2*P + 128]   (direct path)
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   const int ci_t = wi % p.ci_tiles; wi /= p.ci_tiles;
   const int grp = wi;                                   // tap group
   const int split = blockIdx.y, nsplit = gridDim.y;
-  const int ci0 = ci_t * 128, co0 = co_t * p.BN;
+  const int ci0 = ci_t * p.CI, co0 = co_t * p.BN;
   const int taps_hw = p.kh * p.kw;
   // taps of this group: tap = tap0 + g, g in [0, G)
   const int tap0 = grp * p.G;
@@ -208,9 +214,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     if (p.nraw >= 2) {
       // ---- asynchronous path: raw fp32 sub-stages (64 channels of the patch, or 64 channels of the dY tile) are fetched
       // with cp.async one sub-stage ahead, then transformed into the bf16 operand stage of the tile
-      const int l8 = lane & 7, pg = lane >> 3;
       const int CW = p.CW, NQ = CW >> 2, NQs = (CW == 64) ? 4 : 3, RS = CW + 4;   // RS: raw pixel stride (floats), padded
-      const int nA = (min(128, p.Cin - ci0) + CW - 1) / CW, nB = (p.BN + 63) >> 6, nsub = nA + nB;
+      const int nA = (min(p.CI, p.Cin - ci0) + CW - 1) / CW, nB = (p.BN + 63) >> 6, nsub = nA + nB;
+      const uint32_t a_tail = 8u * (uint32_t)p.Ppad * 16u;           // bf16x3: tails of the CTA's 64 channels = GEMM rows 64-127
+      const uint32_t b_tail = (uint32_t)(p.BN >> 3) * 129u * 16u;     //         tails of the BN columns = columns BN..2BN-1
       const int climit = min(p.Cout, co0 + p.BN);
       struct SubIt { long long t; int u, seq; bool done; int n_img, d0, h0, w0; long long m0; };
       auto settle = [&](SubIt& it) {
@@ -381,8 +388,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
                 }
               }
               uint4 o;
-              o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
-              o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+              if (!p.split) {
+                o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
+                o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+              } else {
+                uint4 t;
+                tc::pack_split_bf16x2(va.x, va.y, o.x, t.x); tc::pack_split_bf16x2(va.z, va.w, o.y, t.y);
+                tc::pack_split_bf16x2(vb.x, vb.y, o.z, t.z); tc::pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+                if (qok) *reinterpret_cast<uint4*>(drow + a_tail + (uint32_t)j * (uint32_t)p.Ppad * 16u) = t;
+              }
               if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)j * (uint32_t)p.Ppad * 16u) = o;
             }
           }
@@ -405,8 +419,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
             float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
             if (has && c0 + c < climit) { va = *reinterpret_cast<const float4*>(row + c); vb = *reinterpret_cast<const float4*>(row + c + 4); }
             uint4 o;
-            o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
-            o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+            if (!p.split) {
+              o.x = tc::pack_bf16x2(va.x, va.y); o.y = tc::pack_bf16x2(va.z, va.w);
+              o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
+            } else {
+              uint4 t;
+              tc::pack_split_bf16x2(va.x, va.y, o.x, t.x); tc::pack_split_bf16x2(va.z, va.w, o.y, t.y);
+              tc::pack_split_bf16x2(vb.x, vb.y, o.z, t.z); tc::pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+              *reinterpret_cast<uint4*>(dst + b_tail + (uint32_t)j * 129u * 16u + (uint32_t)q * 16u) = t;
+            }
             *reinterpret_cast<uint4*>(dst + (uint32_t)j * 129u * 16u + (uint32_t)q * 16u) = o;
           }
         }
@@ -479,8 +500,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         }
       }
       uint8_t* dA = sA + st * A_BYTES;
-      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0, p.Cin, dA, 8, warp, lane, p.s2d ? p.s2d_quads : 0);
-      stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0 + 64, p.Cin, dA + 8u * p.Ppad * 16u, 8, warp, lane, p.s2d ? p.s2d_quads : 0);
+      if (p.split) {
+        stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0, p.Cin, dA, 8, warp, lane, p.s2d ? p.s2d_quads : 0, dA + 8u * p.Ppad * 16u);
+      } else {
+        stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0, p.Cin, dA, 8, warp, lane, p.s2d ? p.s2d_quads : 0);
+        stage_block(p.src, p.nsrc, base, of, p.P, p.Ppad, ci0 + 64, p.Cin, dA + 8u * p.Ppad * 16u, 8, warp, lane, p.s2d ? p.s2d_quads : 0);
+      }
       // dY tile: plain tensor, no prologue
       hdn_src dys;
       dys.t = p.dy; dys.pa = nullptr; dys.pb = nullptr; dys.relu = 0;
@@ -491,7 +516,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       uint8_t* dB = sB + st * B_BYTES;
       for (int cb = 0; cb < p.BN; cb += 64)
         stage_block(&dys, 1, dbase, of + 2 * p.P, 128, 129, co0 + cb, min(p.Cout, co0 + p.BN), dB + (uint32_t)(cb / 8) * 129u * 16u,
-                    (p.BN - cb + 7) / 8, warp, lane);
+                    (p.BN - cb + 7) / 8, warp, lane, 0,
+                    p.split ? dB + (uint32_t)((p.BN + cb) / 8) * 129u * 16u : nullptr);
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&full[st]);
       if (++st == NS) { st = 0; ph ^= 1; }
@@ -503,15 +529,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
     const int q4 = warp & 3;                 // TMEM lane quarter this warp may read
-    const int ci = ci0 + q4 * 32 + lane;
+    const int ci = ci0 + (p.split ? ((q4 * 32 + lane) & 63) : (q4 * 32 + lane));   // bf16x3: rows 64-127 are the tails of rows 0-63
     const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const bool vec = (p.Cout % 4 == 0);
     float v[16];
     // a CTA whose tap group never met a valid depth slab issued no MMA: its accumulators are undefined
     for (int g = (warp >> 2); produced && g < p.G; g += 2) {       // warps 0-3 take even taps, warps 4-7 odd
       const int tap = tap0 + g;
-      for (int cc = 0; cc < p.BN; cc += 16) {
-        tc::tmem_ld16(taddr + (uint32_t)(g * p.BN + cc), v);
+      for (int ce = 0; ce < p.BNe; ce += 16) {
+        tc::tmem_ld16(taddr + (uint32_t)(g * p.BNe + ce), v);
+        const int cc = ce >= p.BN ? ce - p.BN : ce;            // bf16x3: columns BN.. are the tail columns of 0..BN-1
         long long wrow = (long long)tap * p.Cin + ci;        // row of dW [tap][ci]
         bool rok = ci < p.Cin;
         if (p.s2d) {
@@ -545,7 +572,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
   } else {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 1, 1);
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.BNe, 1, 1);
       const uint32_t a_lbo = (uint32_t)p.PW * 16u, a_sbo = (uint32_t)p.Ppad * 16u;   // K-group / MN-group strides
       const uint32_t b_lbo = 128u, b_sbo = 129u * 16u;
       int st = 0;
@@ -568,7 +595,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         uint32_t tap_units = tap_units0;                     // ((th - gth0) * PW + (tw - gtw0)) in 16-byte units
         int twc = twc0;
         uint32_t tm = tmem_base;
-        for (int g = 0; g < p.G; ++g, tm += (uint32_t)p.BN) {
+        for (int g = 0; g < p.G; ++g, tm += (uint32_t)p.BNe) {
           const uint64_t ad = ad0 + tap_units;
           tc::umma_bf16(tm, ad, bd0, idesc, acc);            // overwrite only on the very first K step of each tap
 #pragma unroll
@@ -592,6 +619,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
 }
 
 struct WgPlan {
+  int split, BNe, CI;
   int BN, G, groups, ci_tiles, co_tiles, flat, PH, PW, P, Ppad, tiles_h, tiles_w, tmem_cols, row_mode;
   int nraw, raw_bytes, CW, PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], tab_src[2], tab_vq[2], tab_dy, tab_ints;
   long long n_pos_tiles;
@@ -621,21 +649,27 @@ bool wg_plan(const hdn_conv* c, const WgGeom& gm, WgPlan& best) {
   bool up = false;
   for (int i = 0; i < c->nsrc; ++i) up = up || c->src[i].ud != 1 || c->src[i].uh != 1 || c->src[i].uw != 1;
   const int flat = (T == 1 && !up) ? 1 : 0;
-  const int ci_tiles = (gm.Cin + 127) / 128;
+  const int split = c->precision == 2 ? 1 : 0;            // bf16x3: 64 channels (head + tail rows) x 2*BN (head + tail columns)
+  const int CI = split ? 64 : 128;
+  const int ci_tiles = (gm.Cin + CI - 1) / CI;
   double best_cost = 1e300;
   bool found = false;
   const int cand[3] = {taps_hw, gm.kw, 1};       // taps per group: one depth slab, one kernel row, a single tap
   for (int k = 0; k < 3; ++k) {
     const int G = cand[k];
     if (k > 0 && G == cand[k - 1]) continue;
-    int bn_max = (512 / G) / 16 * 16;
-    if (bn_max > 256) bn_max = 256;
-    if (bn_max < 16) continue;
+    int bn_top = (512 / G) / (split ? 2 : 1) / 16 * 16;
+    if (bn_top > (split ? 128 : 256)) bn_top = split ? 128 : 256;
+    if (bn_top < 16) continue;
+    // bf16x3 doubles the dY stage: narrow the column tile until the asynchronous producer's raw ring fits as well
+    for (int bn_max = bn_top; bn_max >= 16; bn_max = split ? (bn_max / 2) / 16 * 16 : 0) {
     WgPlan pl;
+    pl.split = split; pl.CI = CI;
     pl.G = G; pl.groups = T / G; pl.ci_tiles = ci_tiles; pl.flat = flat;
     pl.co_tiles = (c->Cout + bn_max - 1) / bn_max;
     int bn = (c->Cout + pl.co_tiles - 1) / pl.co_tiles;
     pl.BN = (bn + 15) / 16 * 16;
+    pl.BNe = split ? 2 * pl.BN : pl.BN;
     const int rows = (G == taps_hw) ? gm.kh : 1;  // kernel rows covered by a group
     const int cols = (G == 1) ? 1 : gm.kw;
     pl.row_mode = (G == taps_hw) ? 0 : 1;
@@ -649,9 +683,9 @@ bool wg_plan(const hdn_conv* c, const WgGeom& gm, WgPlan& best) {
     const long long M = (long long)c->N * c->D * c->H * c->W;
     pl.n_pos_tiles = flat ? (M + 127) / 128 : (long long)c->N * c->D * pl.tiles_h * pl.tiles_w;
     int cols_t = 32;
-    while (cols_t < G * pl.BN) cols_t *= 2;
+    while (cols_t < G * pl.BNe) cols_t *= 2;
     pl.tmem_cols = cols_t;
-    const size_t a_bytes = 16ull * pl.Ppad * 16, b_bytes = (size_t)((pl.BN + 7) / 8) * 129 * 16;
+    const size_t a_bytes = 16ull * pl.Ppad * 16, b_bytes = (size_t)((pl.BNe + 7) / 8) * 129 * 16;
     // asynchronous producer geometry (not for the space-to-depth stems)
     pl.CW = (c->nsrc == 2) ? 32 : 64;
     int roff = 0, toff = 0;
@@ -680,9 +714,10 @@ bool wg_plan(const hdn_conv* c, const WgGeom& gm, WgPlan& best) {
     }
     pl.smem = fixed + (size_t)pl.nraw * pl.raw_bytes;
     if (pl.smem > 226 * 1024) continue;
-    double cost = (double)pl.ci_tiles * pl.co_tiles * pl.groups * ((double)pl.P * 128 * c->nsrc + 128.0 * pl.BN);
+    double cost = (double)pl.ci_tiles * pl.co_tiles * pl.groups * ((double)pl.P * CI * c->nsrc + 128.0 * pl.BN);
     if (!gm.s2d && pl.nraw == 0) cost *= 4.0;            // falls back to the synchronous producer: much slower
     if (cost < best_cost) { best_cost = cost; best = pl; found = true; }
+    }
   }
   if (!found) return false;
   const long long items = (long long)best.ci_tiles * best.co_tiles * best.groups;
@@ -719,6 +754,17 @@ int hdn_wgrad_tc_supported(const hdn_conv* c) {
   return wg_plan(c, wg_geom(c), pl) ? 1 : 0;
 }
 
+// launch plan of the wgrad kernel (host arithmetic only; see hdn_conv_tc_plan in hdn.h)
+int hdn_wgrad_plan_info(const hdn_conv* c, int* out) {
+  WgPlan pl;
+  if (!wg_plan(c, wg_geom(c), pl)) return HDN_ERR_UNSUPPORTED;
+  out[0] = pl.BN; out[1] = pl.co_tiles; out[2] = pl.ci_tiles; out[3] = pl.CW; out[4] = pl.G; out[5] = pl.nraw;
+  out[6] = pl.tmem_cols; out[7] = (int)pl.smem; out[8] = pl.flat; out[9] = pl.P; out[10] = pl.split;
+  out[11] = hdn_tc_stem(c) ? 1 : 0; out[12] = pl.ci_tiles * pl.co_tiles * pl.groups * pl.splits; out[13] = 1;
+  out[14] = pl.BNe; out[15] = pl.CI;
+  return HDN_OK;
+}
+
 int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   WgPlan pl;
   const WgGeom gm = wg_geom(c);
@@ -736,6 +782,7 @@ int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.pd_lo = gm.pd_lo; p.ph_lo = gm.ph_lo; p.pw_lo = gm.pw_lo;
   p.s2d = gm.s2d; p.s2d_quads = gm.quads; p.cin_real = c->Cin;
   p.Cin = gm.Cin; p.Cout = c->Cout;
+  p.split = pl.split; p.BNe = pl.BNe; p.CI = pl.CI;
   p.BN = pl.BN; p.G = pl.G; p.groups = pl.groups; p.ci_tiles = pl.ci_tiles; p.co_tiles = pl.co_tiles;
   p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad; p.row0_mode = pl.row_mode;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_pos_tiles = pl.n_pos_tiles;

@@ -133,4 +133,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// bf16x3 operand split: (a, b) -> head = bf16_rn(x), tail = bf16_rn(x - head); head + tail carries ~16 significant bits
+__device__ __forceinline__ void pack_split_bf16x2(float a, float b, uint32_t& head, uint32_t& tail) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  head = *reinterpret_cast<const uint32_t*>(&h);
+  tail = pack_bf16x2(a - hf.x, b - hf.y);
+}
+
 }  // namespace tc

@@ -21,6 +21,10 @@ import torch
 from . import _lib
 
 
+# Net(precision=...) -> hdn_conv.precision of the convolutions the tcgen05 path takes (include/hdn.h)
+TC_PRECISION = {"bf16": 1, "bf16x3": 2}
+
+
 # ------------------------------------------------------------------------- descriptors
 class TView(object):
     """Channel window [coff, coff+C) of a Buffer, optionally re-read with other (N, D)."""
@@ -138,7 +142,7 @@ class CudaBackend(object):
 
     @staticmethod
     def _conv_key(d, what):
-        return "conv_%s[%s] k%dx%dx%d" % (what, "tc" if d.precision else "simt", d.k[0], d.k[1], d.k[2])
+        return "conv_%s[%s] k%dx%dx%d" % (what, ("simt", "tc", "tc-x3")[d.precision], d.k[0], d.k[1], d.k[2])
 
     @staticmethod
     def _conv_flops(d):
@@ -523,10 +527,11 @@ class ConvOp(object):
                              srcs=self.srcs, w=self.w.t, bias=None if self.bias is None else self.bias.t, stat=st,
                              drop_keep=1.0 - self.drop_rate, drop_seed=0, precision=0)
         self.prec = [0, 0, 0]
-        if net.precision == "bf16":
-            self.desc.precision = 1
+        if net.precision in TC_PRECISION:
+            # tensor-core path: 1 = bf16 operands, 2 = bf16x3 (head + tail split, fp32-grade results); fp32 accumulation
+            self.desc.precision = TC_PRECISION[net.precision]
             for i in range(3):
-                self.prec[i] = 1 if net.be.conv_tc_supported(self.desc, i) else 0
+                self.prec[i] = self.desc.precision if net.be.conv_tc_supported(self.desc, i) else 0
                 if self.prec[i]:
                     net.ws_need = max(net.ws_need, net.be.conv_tc_workspace(self.desc, i))
             self.desc.precision = 0

@@ -71,8 +71,10 @@ typedef struct {
   double* stat_sq;        /* [Cout] += sum_m y^2 */
   float drop_keep;        /* 1.0 => no dropout; else y = y*mask/keep (KB:2888) */
   uint64_t drop_seed;
-  int precision;          /* 0: fp32 FMA (parity path)  1: tcgen05 bf16 operands, fp32 accumulate */
-  void* ws;               /* precision 1: device scratch for the packed bf16 weight blocks of this call */
+  int precision;          /* 0: fp32 FMA (parity path)  1: tcgen05 bf16 operands, fp32 accumulate
+                             2: tcgen05 "bf16x3": operands split into bf16 head + tail, 3 MMAs per step
+                                (hi*hi + lo*hi + hi*lo), fp32 accumulate -- fp32-grade results */
+  void* ws;               /* precision 1/2: device scratch for the packed bf16 weight blocks of this call */
   int64_t ws_bytes;       /*   >= hdn_conv_tc_workspace(c, pass); may be shared by all calls of one stream */
 } hdn_conv;
 
@@ -102,6 +104,15 @@ int hdn_conv_wgrad(const hdn_conv* c, float* dw, float* dbias, void* stream);
 int hdn_conv_tc_supported(const hdn_conv* c, int pass /*0 fprop 1 dgrad 2 wgrad*/);
 /* Bytes of hdn_conv.ws the tcgen05 path needs for this descriptor and pass (0 if unsupported). */
 int64_t hdn_conv_tc_workspace(const hdn_conv* c, int pass);
+
+/* Launch plan the tcgen05 path would use for this descriptor and pass (host arithmetic only, no device
+ * access): out16 = { BN (column tile), column tiles, K blocks (fprop/dgrad) or input-channel tiles (wgrad),
+ * channels per stage, weight-ring depth (fprop/dgrad) or taps per group (wgrad), raw fp32 ring depth,
+ * TMEM columns, dynamic shared memory bytes, flat (1x1x1) flag, patch pixels, bf16x3 flag, space-to-depth
+ * flag, work items, copy-list-fits flag, GEMM K (fprop/dgrad) or GEMM N (wgrad), GEMM columns (fprop/dgrad)
+ * or input channels per CTA (wgrad) }.  Used by the host-side tests to check every convolution of a model
+ * against the SM's limits (227 KB shared memory, 512 TMEM columns) without a GPU. */
+int hdn_conv_tc_plan(const hdn_conv* c, int pass, int32_t* out16);
 
 /* Pooling (KB:3354-3432).  kind 0: max 3x3(x3)/2 after zero-pad 1 (the ZeroPadding + VALID
  * max-pool of hybridnet.py:128-129,215-216; input passes through the src prologue first);

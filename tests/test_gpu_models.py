@@ -229,3 +229,42 @@ def test_hybrid_train_step_bf16_tensor_cores(cuda_dev):
         if e > 0.25 or cos < 0.97:
             bad.append((k, e, cos))
     assert not bad, bad[:8]
+
+
+def test_hybrid_train_step_bf16x3_tensor_cores(cuda_dev):
+    """precision="bf16x3": every convolution on the tcgen05 path with both operands split into a bf16 head and a
+    bf16 tail (hi*hi + lo*hi + hi*lo, fp32 accumulation).  This is the tensor-core configuration that meets the
+    north-star parity bound: logits rel-L2 <= 1e-3 and loss rel <= 1e-3 against the fp32 oracle, parameter gradients
+    under the same bound as the fp32 FMA path (max(5e-3, 8x the fp32 oracle's own distance from the fp64 oracle))."""
+    a = Args(b=1, input_size=64, input_cols=8)
+    m = hdn.dense_rnn_net(a, precision="bf16x3")
+    m.dropout = False
+    perturb_params(m)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+    vol, lab = synthetic_slab(1, 64, 8)
+    w0 = m.get_weights_dict()
+    og, ol, olog = {}, {}, {}
+    for dt in (torch.float32, torch.float64):
+        ctx, logits = orc.forward_hybrid(w0, vol, training=True, variant="end2end", requires_grad=True, dtype=dt)
+        loss = orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), logits, crop=True)
+        og[dt], ol[dt], olog[dt] = orc.grads_of(ctx, loss), float(loss.detach()), logits.detach().numpy()
+    got_loss = m.train_on_batch(vol, lab)
+    net = m.nets[True]
+    assert all(p[0] == 2 for _, p in net.report), "a convolution's fprop left the bf16x3 tensor-core path"
+    assert sum(1 for _, p in net.report if all(x == 2 for x in p)) >= len(net.report) - 2   # 3-class classifiers: dgrad/wgrad fp32
+    err = rel_l2(m._logits_to_host(net), olog[torch.float32])
+    assert err < 1e-3, err
+    assert abs(got_loss - ol[torch.float32]) <= 1e-3 * abs(ol[torch.float32])
+    trainable = sorted(p.name for p in m.params.order if p.trainable)
+    _grad_check(m.get_grads_dict(), og[torch.float32], og[torch.float64], trainable, 5e-3)
+    # inference program: Dice of the thresholded masks identical to 4 d.p. (test.py:34-35,73-77)
+    out = m.predict(vol)
+    _, l2 = orc.forward_hybrid(m.get_weights_dict(), vol, training=False, variant="end2end")
+    assert rel_l2(out, l2.numpy()) < 1e-3
+    pe = torch.softmax(torch.as_tensor(out), -1).numpy()
+    po = torch.softmax(l2, -1).numpy()
+    for cls, thr in ((1, 0.5), (2, 0.9)):
+        keep = np.abs(po[..., cls] - thr) > 1e-4
+        de = orc.dice((pe[..., cls] > thr) & keep, (lab[..., 0] == cls) & keep)
+        do = orc.dice((po[..., cls] > thr) & keep, (lab[..., 0] == cls) & keep)
+        assert round(de, 4) == round(do, 4)

@@ -1,8 +1,11 @@
-"""tcgen05 convolution kernels (precision 1: bf16 operands, fp32 TMEM accumulation) against the fp32
-FMA kernels of the same C-ABI call on identical descriptors: fprop (output, bias, dropout mask, batch
-statistics), dgrad (dx / du, ReLU mask, S1/S2 sums, up-sampling reduction, two sources) and wgrad.
-Tolerance: operands are rounded to bf16 (2^-9 relative), accumulation is fp32, so a correct kernel sits at
-~3e-3 rel-L2 from the fp32 result; the bound used is 1.5e-2.  A layout / descriptor error gives O(1)."""
+"""tcgen05 convolution kernels (precision 1: bf16 operands; precision 2: "bf16x3", operands split into a bf16
+head and tail, three MMAs per K step; fp32 TMEM accumulation in both) against the fp32 FMA kernels of the same
+C-ABI call on identical descriptors: fprop (output, bias, dropout mask, batch statistics), dgrad (dx / du, ReLU
+mask, S1/S2 sums, up-sampling reduction, two sources) and wgrad.
+Tolerance, precision 1: operands are rounded to bf16 (2^-9 relative), accumulation is fp32, so a correct kernel
+sits at ~3e-3 rel-L2 from the fp32 result; the bound used is 1.5e-2.  Precision 2: head + tail carry ~16
+significant bits and only the tail x tail product (2^-18) is dropped, so a correct kernel sits at ~1e-5; the
+bound is 1e-4 (a missing cross term shows up at ~1e-3).  A layout / descriptor error gives O(1)."""
 import numpy as np
 import pytest
 import torch
@@ -12,7 +15,9 @@ from h_denseunet_b200.engine import Act, EpiDesc, Src
 from util import rel_l2
 
 pytestmark = pytest.mark.gpu
-TOL = 1.5e-2
+TOLS = {1: 1.5e-2, 2: 1e-4}
+TC_NAME = {1: "bf16", 2: "bf16x3"}
+PRECS = [pytest.param(1, id="bf16"), pytest.param(2, id="bf16x3")]
 
 
 def _rand_fold_params(ps, rng):
@@ -36,9 +41,9 @@ class Case(object):
     output window inside a wider buffer."""
 
     def __init__(self, dev, N, D, H, W, cin, cout, k, ups=((1, 1, 1),), fold=(True,), bias=False, stats=False,
-                 drop=0.0, src_pad=16, out_pad=32, seed=0, stride=(1, 1, 1), src_c=None):
+                 drop=0.0, src_pad=16, out_pad=32, seed=0, stride=(1, 1, 1), src_c=None, tc=1):
         rng = np.random.default_rng(seed)
-        self.net = net = engine.Net(engine.ParamStore(seed), dev, True, "bf16", dropout=drop > 0)
+        self.net = net = engine.Net(engine.ParamStore(seed), dev, True, TC_NAME[tc], dropout=drop > 0)
         srcs = []
         self.src_bufs = []
         for i, up in enumerate(ups):
@@ -131,14 +136,16 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_fprop_tc_vs_fp32(cuda_dev, name):
+def test_fprop_tc_vs_fp32(cuda_dev, name, prec):
     kw = dict(CASES[name])
     kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
-    c = Case(cuda_dev, **kw)
-    assert c.supported[0] == 1, "tcgen05 fprop does not take %s" % name
+    c = Case(cuda_dev, tc=prec, **kw)
+    assert c.supported[0] == prec, "tcgen05 fprop does not take %s" % name
+    TOL = TOLS[prec]
     y0, s0, _ = c.fprop(0)
-    y1, s1, untouched = c.fprop(1)
+    y1, s1, untouched = c.fprop(prec)
     assert untouched == 0.0, "wrote outside the output channel window"
     err = rel_l2(y1, y0)
     assert err < TOL, (name, err)
@@ -146,17 +153,19 @@ def test_fprop_tc_vs_fp32(cuda_dev, name):
         assert rel_l2(s1[0], s0[0]) < TOL and rel_l2(s1[1], s0[1]) < TOL
 
 
-def test_fprop_tc_dropout_mask_identical(cuda_dev):
+@pytest.mark.parametrize("prec", PRECS)
+def test_fprop_tc_dropout_mask_identical(cuda_dev, prec):
     kw = dict(CASES["3x3x3_up222_bias_stats"])
     kw.update(drop=0.3, stats=False, fold=(True,))
-    c = Case(cuda_dev, **kw)
+    c = Case(cuda_dev, tc=prec, **kw)
+    TOL = TOLS[prec]
     c.op.desc.drop_seed = 12345
     for key in ("_c_f", "_c_g"):
         c.op.desc.__dict__.pop(key, None)
     net_seed = c.net.step_seed
     c.net.step_seed = lambda name: 12345
     y0, _, _ = c.fprop(0)
-    y1, _, _ = c.fprop(1)
+    y1, _, _ = c.fprop(prec)
     c.net.step_seed = net_seed
     assert np.array_equal(y0 == 0, y1 == 0)
     assert abs(float((y0 == 0).mean()) - 0.3) < 0.02
@@ -167,18 +176,20 @@ DG = ["stem3d_7x7x7s2", "1x1_flat", "1x1_flat_tail", "3x3_dense", "3x3x3_dense",
       "3x3x3_up122_504", "3x3x3_two_src"]
 
 
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", DG)
 @pytest.mark.parametrize("mode,accumulate", [(0, False), (0, True), (1, False), (1, True)])
-def test_dgrad_tc_vs_fp32(cuda_dev, name, mode, accumulate):
+def test_dgrad_tc_vs_fp32(cuda_dev, name, mode, accumulate, prec):
     kw = dict(CASES[name])
     kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
-    c = Case(cuda_dev, **kw)
-    assert c.supported[1] == 1, "tcgen05 dgrad does not take %s" % name
+    c = Case(cuda_dev, tc=prec, **kw)
+    assert c.supported[1] == prec, "tcgen05 dgrad does not take %s" % name
+    TOL = TOLS[prec]
     stem = name.startswith("stem")        # a stem input has no BN in front: plain dx, no S1/S2 (engine.Planner.epilogue_for)
     if stem and mode == 1:
         pytest.skip("stem inputs never take the du form")
     r0 = c.dgrad(0, mode, accumulate, with_sums=not stem)
-    r1 = c.dgrad(1, mode, accumulate, with_sums=not stem)
+    r1 = c.dgrad(prec, mode, accumulate, with_sums=not stem)
     for (g0, S0), (g1, S1) in zip(r0, r1):
         assert rel_l2(g1, g0) < TOL, (name, mode, accumulate, rel_l2(g1, g0))
         assert rel_l2(S1[0], S0[0]) < TOL and rel_l2(S1[1], S0[1]) < TOL
@@ -194,15 +205,17 @@ def _wgrad(c, prec):
     return op.w.g.cpu().numpy().copy(), None if op.bias is None else op.bias.g.cpu().numpy().copy()
 
 
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_wgrad_tc_vs_fp32(cuda_dev, name):
+def test_wgrad_tc_vs_fp32(cuda_dev, name, prec):
     kw = dict(CASES[name])
     kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
-    c = Case(cuda_dev, **kw)
-    if c.supported[2] != 1:
+    c = Case(cuda_dev, tc=prec, **kw)
+    if c.supported[2] != prec:
         pytest.skip("tcgen05 wgrad does not take %s" % name)
+    TOL = TOLS[prec]
     w0, b0 = _wgrad(c, 0)
-    w1, b1 = _wgrad(c, 1)
+    w1, b1 = _wgrad(c, prec)
     assert rel_l2(w1, w0) < TOL, (name, rel_l2(w1, w0))
     if b0 is not None:
         assert rel_l2(b1, b0) < 1e-4

@@ -24,6 +24,7 @@
 //   warp 9     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //              TMEM accumulator buffers and releases stages with tcgen05.commit.
 //   warps 10-13 epilogue: tcgen05.ld the finished accumulator while the next tile's MMAs run.
+#include <stdlib.h>
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
@@ -70,6 +71,7 @@ struct TcParams {
   hdn_src src[2];             // A operand sources
   const __nv_bfloat16* wpack;
   int mode;                   // 0 fprop, 1 dgrad
+  int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
   int pd_lo, ph_lo, pw_lo;    // patch origin = tile origin - p*_lo (padding in front of tap 0)
   int s2d;                    // 1: A operand is the space-to-depth view of a stride-2 convolution's input:
@@ -393,6 +395,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const bool pa1 = two && p.src[1].pa != nullptr, pb1 = two && p.src[1].pb != nullptr, relu1 = two && p.src[1].relu != 0;
           const int nch = p.CK >> 3, nhalf = nch >> 1;           // chunks per stage (8 or 4); a work item = 32 pixels x half of them
           const int nitems = ((p.P + 31) >> 5) * 2;
+          // warp-per-chunk form for the two prologue shapes that cover all single-source operands of the networks:
+          // BN -> Scale -> ReLU (every dense-block / transition / decoder input) and none (dY in dgrad)
+          const int xmode = two ? -1 : ((pa0 && pb0 && relu0) ? 1 : ((!pa0 && !pb0 && !relu0) ? 0 : -1));
+          if (p.fastx && xmode >= 0) {
+            const int j = warp & (nch - 1), c = j * 8;          // this warp's chunk; 8 / nch warps share a chunk's pixels
+            tc::xform_chunk_any(xmode, p.split != 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
+                                ab0 + c, ab0 + p.CK + c, c0 + c < p.K, dst + (uint32_t)j * (uint32_t)p.Ppad * 16u,
+                                dst + (uint32_t)(nch + j) * (uint32_t)p.Ppad * 16u);
+          } else
           for (int item = warp; item < nitems; item += 8) {
             const int q = (item >> 1) * 32 + lane;
             const int j0 = (item & 1) * nhalf;
@@ -954,6 +965,20 @@ __global__ void __launch_bounds__(256) zero_window_kernel(hdn_tensor t, long lon
   }
 }
 
+}  // namespace
+
+// HDN_TC_FASTX=0/1 selects the operand-transform form of the tcgen05 kernels (read once per process)
+int hdn_tc_fastx() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDN_TC_FASTX");
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  return v;
+}
+
+namespace {
+
 struct TcPlan {
   int BN, n_tiles, KB, CK, nsb, nraw, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
   int PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], raw_bytes, tab_src[2], tab_vq[2], tab_ints;
@@ -1129,6 +1154,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.wpack = wp;
   p.mode = mode;
   p.split = nsplit == 2 ? 1 : 0;
+  p.fastx = hdn_tc_fastx();
   if (mode == 0) {
     p.nsrc = c->nsrc;
     p.src[0] = c->src[0];

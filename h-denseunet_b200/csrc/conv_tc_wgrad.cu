@@ -22,6 +22,7 @@
 #include "tc_common.cuh"
 
 int hdn_tc_stem(const hdn_conv* c);   // conv_tc.cu
+int hdn_tc_fastx();                   // conv_tc.cu
 
 namespace {
 
@@ -35,6 +36,7 @@ struct WgParams {
   int kd, kh, kw;
   int Cin, Cout;
   int BN, G, groups;           // column tile, taps per group, number of tap groups
+  int fastx;                   // 1: warp-per-chunk operand transform (tc::xform_chunk)
   int split, BNe, CI;          // bf16x3 folding: BNe = GEMM N (2*BN when split), CI = input channels per CTA (64 when split, else 128)
   int ci_tiles, co_tiles;
   int flat;
@@ -346,6 +348,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           const int relu1 = two ? p.src[1].relu : 0;
           const int nhalf = CW >> 4;                             // chunks per work item (half of the sub-stage's chunks)
           const int nitems = ((p.P + 31) >> 5) * 2;
+          const int xmode = two ? -1 : ((pa0 && pb0 && relu0 != 0) ? 1 : ((!pa0 && !pb0 && relu0 == 0) ? 0 : -1));
+          if (p.fastx && xmode >= 0) {
+            // warp-per-chunk form (tc::xform_chunk): the chunk's (a, b) stay in registers for the whole sub-stage
+            const int nch = CW >> 3, j = warp & (nch - 1), c = j * 8;
+            tc::xform_chunk_any(xmode, p.split != 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
+                                ab0 + c, ab0 + CW + c, c0 + c < p.Cin, dst + (uint32_t)j * (uint32_t)p.Ppad * 16u,
+                                dst + a_tail + (uint32_t)j * (uint32_t)p.Ppad * 16u);
+          } else
           for (int item = warp; item < nitems; item += 8) {
             const int q = (item >> 1) * 32 + lane;
             const int j0 = (item & 1) * nhalf;
@@ -783,6 +793,7 @@ int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.s2d = gm.s2d; p.s2d_quads = gm.quads; p.cin_real = c->Cin;
   p.Cin = gm.Cin; p.Cout = c->Cout;
   p.split = pl.split; p.BNe = pl.BNe; p.CI = pl.CI;
+  p.fastx = hdn_tc_fastx();
   p.BN = pl.BN; p.G = pl.G; p.groups = pl.groups; p.ci_tiles = pl.ci_tiles; p.co_tiles = pl.co_tiles;
   p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad; p.row0_mode = pl.row_mode;
   p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.n_pos_tiles = pl.n_pos_tiles;

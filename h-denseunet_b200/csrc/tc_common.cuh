@@ -141,4 +141,72 @@ __device__ __forceinline__ void pack_split_bf16x2(float a, float b, uint32_t& he
   tail = pack_bf16x2(a - hf.x, b - hf.y);
 }
 
+// Operand transform, warp-per-chunk form: one warp turns ONE 8-channel chunk of a raw fp32 stage (pixel stride RS
+// floats) into bf16 for the pixels q0, q0 + qstep, ... (lane = pixel).  The chunk's per-channel (a, b) are read once and
+// stay in registers for the whole stage, and the prologue form is a compile-time constant, so a pixel costs two 16-byte
+// reads, 8 FFMA + 8 FMNMX (MODE 1), 4 packs and one 16-byte store.
+//   MODE 0: y = x            MODE 1: y = max(a*x + b, 0)   (BatchNorm -> Scale -> ReLU folded; hdn_src.pa/pb/relu all set)
+//   SPLIT : also store the bf16 tail (x - head) at dtail (bf16x3)
+// vq[q] = source-patch pixel of virtual pixel q, or -1 => zero padding (applied after the prologue, like ZeroPadding).
+template <int MODE, bool SPLIT>
+__device__ __forceinline__ void xform_px(float4 va, float4 vb, const float4& a0, const float4& a1, const float4& b0,
+                                         const float4& b1, bool ok, uint4& o, uint4& t) {
+  if (MODE == 1) {
+    va.x = fmaxf(fmaf(a0.x, va.x, b0.x), 0.f); va.y = fmaxf(fmaf(a0.y, va.y, b0.y), 0.f);
+    va.z = fmaxf(fmaf(a0.z, va.z, b0.z), 0.f); va.w = fmaxf(fmaf(a0.w, va.w, b0.w), 0.f);
+    vb.x = fmaxf(fmaf(a1.x, vb.x, b1.x), 0.f); vb.y = fmaxf(fmaf(a1.y, vb.y, b1.y), 0.f);
+    vb.z = fmaxf(fmaf(a1.z, vb.z, b1.z), 0.f); vb.w = fmaxf(fmaf(a1.w, vb.w, b1.w), 0.f);
+  }
+  if (SPLIT) {
+    pack_split_bf16x2(va.x, va.y, o.x, t.x); pack_split_bf16x2(va.z, va.w, o.y, t.y);
+    pack_split_bf16x2(vb.x, vb.y, o.z, t.z); pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+    if (!ok) t = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    o.x = pack_bf16x2(va.x, va.y); o.y = pack_bf16x2(va.z, va.w);
+    o.z = pack_bf16x2(vb.x, vb.y); o.w = pack_bf16x2(vb.z, vb.w);
+  }
+  if (!ok) o = make_uint4(0u, 0u, 0u, 0u);                // zero padding / channels past K: applied after the prologue
+}
+template <int MODE, bool SPLIT>
+__device__ __forceinline__ void xform_chunk(const float* rawc, int RS, const int* vq, int P, int q0, int qstep,
+                                            const float* a8, const float* b8, bool cvalid, uint8_t* dchunk, uint8_t* dtail) {
+  float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), a1 = a0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (MODE == 1) {
+    a0 = *reinterpret_cast<const float4*>(a8); a1 = *reinterpret_cast<const float4*>(a8 + 4);
+    b0 = *reinterpret_cast<const float4*>(b8); b1 = *reinterpret_cast<const float4*>(b8 + 4);
+  }
+  // two pixels per trip, branch-free (a padded pixel reads row 0 and is zeroed by a select), so the four 16-byte
+  // reads of a trip are in flight together: the producers are few warps per scheduler and otherwise latency-bound
+  for (int q = q0; q < P; q += 2 * qstep) {
+    const int qb = q + qstep;
+    const bool hasb = qb < P;
+    const int sqa = vq[q], sqb = hasb ? vq[qb] : -1;
+    const float* rowa = rawc + max(sqa, 0) * RS;
+    const float* rowb = rawc + max(sqb, 0) * RS;
+    const float4 xa0 = *reinterpret_cast<const float4*>(rowa), xa1 = *reinterpret_cast<const float4*>(rowa + 4);
+    const float4 xb0 = *reinterpret_cast<const float4*>(rowb), xb1 = *reinterpret_cast<const float4*>(rowb + 4);
+    uint4 oa, ta, ob, tb;
+    xform_px<MODE, SPLIT>(xa0, xa1, a0, a1, b0, b1, sqa >= 0 && cvalid, oa, ta);
+    xform_px<MODE, SPLIT>(xb0, xb1, a0, a1, b0, b1, sqb >= 0 && cvalid, ob, tb);
+    *reinterpret_cast<uint4*>(dchunk + (uint32_t)q * 16u) = oa;
+    if (SPLIT) *reinterpret_cast<uint4*>(dtail + (uint32_t)q * 16u) = ta;
+    if (hasb) {
+      *reinterpret_cast<uint4*>(dchunk + (uint32_t)qb * 16u) = ob;
+      if (SPLIT) *reinterpret_cast<uint4*>(dtail + (uint32_t)qb * 16u) = tb;
+    }
+  }
+}
+// dispatch on the two runtime-uniform switches
+__device__ __forceinline__ void xform_chunk_any(int mode, bool split, const float* rawc, int RS, const int* vq, int P, int q0,
+                                                int qstep, const float* a8, const float* b8, bool cvalid, uint8_t* dchunk,
+                                                uint8_t* dtail) {
+  if (mode == 1) {
+    if (split) xform_chunk<1, true>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    else       xform_chunk<1, false>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+  } else {
+    if (split) xform_chunk<0, true>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    else       xform_chunk<0, false>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+  }
+}
+
 }  // namespace tc

@@ -241,7 +241,7 @@ def run_gpu(a):
     line = {
         "metric": METRIC, "value": value, "unit": "slabs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if a.precision in ("bf16", "bf16x3") and ntc else "f32", "data": "synthetic",
+        "dtype": "bf16" if a.precision in ("bf16", "bf16x3", "mixed") and ntc else "f32", "data": "synthetic",
         "config": {"workload": "H-DenseUNet end2end train step (hybridnet.dense_rnn_net): %d slab(s)/GPU of %dx%dx%d, "
                                "fwd + weighted CE + bwd + Nesterov SGD%s" % (
                                    a.batch, a.size, a.size, a.cols, " + P2P grad reduce" if world > 1 else ""),
@@ -317,9 +317,9 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cols", type=int, default=48)
     ap.add_argument("--batch", type=int, default=2, help="slabs per GPU (north star: 2)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp32"],
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "mixed", "fp32"],
                     help="bf16: tcgen05, operands rounded to bf16; bf16x3: tcgen05, operands split into bf16 head + tail "
-                         "(3 MMAs per step, fp32-grade results); fp32: FMA parity path")
+                         "(3 MMAs per step, fp32-grade results); mixed: fprop + dgrad bf16x3, wgrad bf16; fp32: FMA parity path")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=1)

@@ -397,8 +397,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int nitems = ((p.P + 31) >> 5) * 2;
           // warp-per-chunk form for the two prologue shapes that cover all single-source operands of the networks:
           // BN -> Scale -> ReLU (every dense-block / transition / decoder input) and none (dY in dgrad)
-          const int xmode = two ? -1 : ((pa0 && pb0 && relu0) ? 1 : ((!pa0 && !pb0 && !relu0) ? 0 : -1));
-          if (p.fastx && xmode >= 0) {
+          const int xmode = (pa0 && pb0 && relu0) ? 1 : ((!pa0 && !pb0 && !relu0) ? 0 : -1);
+          const int xmode1 = !two ? -1 : ((pa1 && pb1 && relu1) ? 1 : ((!pa1 && !pb1 && !relu1) ? 0 : -1));
+          const bool fast2 = p.fastx >= 2 && two && xmode1 == 1 && xmode >= 0;      // shapes xform_chunk2_any takes
+          if (fast2) {
+            const int j = warp & (nch - 1), c = j * 8;
+            tc::xform_chunk2_any(xmode, xmode1, p.split != 0, rawf0 + c, rawf1 + c, RS, vq0, vq1, p.P, (warp / nch) * 32 + lane,
+                                 (8 / nch) * 32, ab0 + c, ab0 + p.CK + c, ab1 + c, ab1 + p.CK + c, c0 + c < p.K,
+                                 dst + (uint32_t)j * (uint32_t)p.Ppad * 16u, dst + (uint32_t)(nch + j) * (uint32_t)p.Ppad * 16u);
+          } else if (p.fastx && !two && xmode >= 0) {
             const int j = warp & (nch - 1), c = j * 8;          // this warp's chunk; 8 / nch warps share a chunk's pixels
             tc::xform_chunk_any(xmode, p.split != 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
                                 ab0 + c, ab0 + p.CK + c, c0 + c < p.K, dst + (uint32_t)j * (uint32_t)p.Ppad * 16u,
@@ -967,12 +974,14 @@ __global__ void __launch_bounds__(256) zero_window_kernel(hdn_tensor t, long lon
 
 }  // namespace
 
-// HDN_TC_FASTX=0/1 selects the operand-transform form of the tcgen05 kernels (read once per process)
+// HDN_TC_FASTX=0/1/2 selects the operand-transform form of the tcgen05 kernels (read once per process; default 1,
+// validated on B200 in round 1: profiles/r01b_*)
 int hdn_tc_fastx() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("HDN_TC_FASTX");
-    v = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+    v = e ? atoi(e) : 1;                  // 0 generic, 1 single-source warp-per-chunk form, 2 also the two-source form
+    if (v < 0 || v > 2) v = 1;
   }
   return v;
 }

@@ -1,6 +1,7 @@
 // HBM-bound kernels around the convolutions: pooling, BatchNorm fold / backward, dropout
 // backward, the fused weighted cross-entropy, hybrid glue, Nesterov SGD, sliding-window
 // accumulation.  All are grid-stride, channel-fastest (coalesced on the NDHWC layout).
+#include <stdlib.h>
 #include "hdn_common.cuh"
 
 namespace {
@@ -140,6 +141,87 @@ __global__ void __launch_bounds__(ET) maxpool_bwd_idx(const hdn_pool p, const hd
     float du = (s.relu && !(fmaf(a, x, b) > 0.f)) ? 0.f : dz;
     if (e.s1 && du != 0.f) { atomicAdd(&bins[c], du); atomicAdd(&bins[p.C + c], du * (x - (e.center ? __ldg(e.center + c) : 0.f))); }
     epi_store(e, m, c, p.C, a, du);
+  }
+  if (e.s1) bins_flush(bins, p.C, e.s1, e.s2);
+}
+
+// Same backward, four channels per thread: a thread keeps one channel quad for its whole life (quad = tid % (C/4)), so
+// S1/S2 are plain register sums flushed once, positions are decoded with 32-bit arithmetic once per quad instead of
+// five 64-bit divisions per element, and every access is a 16-byte (or 4-byte arg-max) vector.  Needs C % 4 == 0,
+// 16-byte aligned windows and M < 2^31 (checked by the caller).
+__global__ void __launch_bounds__(ET) maxpool_bwd_idx_v4(const hdn_pool p, const hdn_dgrad_epi e, const unsigned M_in) {
+  extern __shared__ float bins[];
+  const hdn_src& s = p.src;
+  if (e.s1) bins_init(bins, p.C);
+  const unsigned cq = (unsigned)p.C >> 2, ppb = ET / cq;               // quads per position, positions per block pass
+  const unsigned quad = threadIdx.x % cq, pl = threadIdx.x / cq;
+  const int c = (int)quad * 4;
+  float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f), ctr = b;
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pl < ppb) {
+    if (s.pa) a = __ldg(reinterpret_cast<const float4*>(s.pa + c));
+    if (s.pb) b = __ldg(reinterpret_cast<const float4*>(s.pb + c));
+    if (e.s1 && e.center) ctr = __ldg(reinterpret_cast<const float4*>(e.center + c));
+    const unsigned sD = (unsigned)s.D, sH = (unsigned)s.H, sW = (unsigned)s.W;
+    for (unsigned m = blockIdx.x * ppb + pl; m < M_in; m += gridDim.x * ppb) {
+      unsigned r = m;
+      const int iw = (int)(r % sW); r /= sW;
+      const int ih = (int)(r % sH); r /= sH;
+      const int id = (int)(r % sD);
+      const int n = (int)(r / sD);
+      float dz[4] = {0.f, 0.f, 0.f, 0.f};
+      const int odl = p.pool_d ? id / 2 : id, odh = p.pool_d ? (id + 1) / 2 : id;
+      for (int od = odl; od <= odh; ++od) {
+        if (od >= p.D) continue;
+        const int td = p.pool_d ? id - (2 * od - 1) : 0;
+        for (int oh = ih / 2; oh <= (ih + 1) / 2; ++oh) {
+          if (oh >= p.H) continue;
+          const int th = ih - (2 * oh - 1);
+          for (int ow = iw / 2; ow <= (iw + 1) / 2; ++ow) {
+            if (ow >= p.W) continue;
+            const int tw = iw - (2 * ow - 1);
+            const unsigned char tap = (unsigned char)((td * 3 + th) * 3 + tw);
+            const int64_t mo = (((int64_t)n * p.D + od) * p.H + oh) * p.W + ow;
+            const uchar4 t4 = *reinterpret_cast<const uchar4*>(p.argidx + mo * p.C + c);
+            if (t4.x == tap || t4.y == tap || t4.z == tap || t4.w == tap) {
+              const float4 y4 = __ldg(reinterpret_cast<const float4*>(p.y.p + mo * p.y.ldc + p.y.coff + c));
+              if (t4.x == tap) dz[0] += y4.x;
+              if (t4.y == tap) dz[1] += y4.y;
+              if (t4.z == tap) dz[2] += y4.z;
+              if (t4.w == tap) dz[3] += y4.w;
+            }
+          }
+        }
+      }
+      const float4 x4 = __ldg(reinterpret_cast<const float4*>(s.t.p + (int64_t)m * s.t.ldc + s.t.coff + c));
+      const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w};
+      const float cs[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+      float du[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        du[k] = (s.relu && !(fmaf(as[k], xs[k], bs[k]) > 0.f)) ? 0.f : dz[k];
+        s1[k] += du[k];
+        s2[k] += du[k] * (xs[k] - cs[k]);
+      }
+      if (e.mode == 0) {
+        float4* q = reinterpret_cast<float4*>((float*)e.dx.p + (int64_t)m * e.dx.ldc + e.dx.coff + c);
+        float4 g = make_float4(as[0] * du[0], as[1] * du[1], as[2] * du[2], as[3] * du[3]);
+        if (e.accumulate) { const float4 o = *q; g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+        *q = g;
+      } else {
+        float4* q = reinterpret_cast<float4*>(e.du + (int64_t)m * p.C + c);
+        float4 g = make_float4(du[0], du[1], du[2], du[3]);
+        if (e.accumulate) { const float4 o = *q; g.x += o.x; g.y += o.y; g.z += o.z; g.w += o.w; }
+        *q = g;
+      }
+    }
+    if (e.s1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (s1[k] != 0.f) atomicAdd(&bins[c + k], s1[k]);
+        if (s2[k] != 0.f) atomicAdd(&bins[p.C + c + k], s2[k]);
+      }
+    }
   }
   if (e.s1) bins_flush(bins, p.C, e.s1, e.s2);
 }
@@ -415,6 +497,19 @@ __global__ void __launch_bounds__(ET) window_fin_kernel(float* __restrict__ scor
 
 #define ST ((cudaStream_t)stream)
 
+// HDN_POOL_FAST=0/1: four-channels-per-thread max-pool backward (read once per process)
+static int hdn_pool_fast() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDN_POOL_FAST");
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  return v;
+}
+static bool aligned16(const hdn_tensor& t) {
+  return t.ldc % 4 == 0 && t.coff % 4 == 0 && (reinterpret_cast<uintptr_t>(t.p) & 15) == 0;
+}
+
 extern "C" int hdn_pool_fwd(const hdn_pool* p, void* stream) {
   HDN_CHECK_ARG(p && p->src.t.p && p->y.p, "pool_fwd: null pointer");
   HDN_CHECK_ARG(p->kind == 0 || p->kind == 1, "pool: kind must be 0 (max) or 1 (avg)");
@@ -429,7 +524,20 @@ extern "C" int hdn_pool_bwd(const hdn_pool* p, const hdn_dgrad_epi* e, void* str
   const int64_t total = (int64_t)p->N * p->src.D * p->src.H * p->src.W * p->C;
   HDN_CHECK_ARG(p->C <= 4096, "pool_bwd: C > 4096 unsupported");
   const size_t sm = e->s1 ? 2 * (size_t)p->C * sizeof(float) : 0;
-  if (p->kind == 0 && p->argidx) maxpool_bwd_idx<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
+  const int64_t M_in = (int64_t)p->N * p->src.D * p->src.H * p->src.W;
+  const bool v4 = hdn_pool_fast() && p->kind == 0 && p->argidx && p->C % 4 == 0 && p->C / 4 <= ET && M_in < (1ll << 31) &&
+                  aligned16(p->src.t) && aligned16(p->y) &&
+                  (e->mode == 0 ? aligned16(e->dx) : (reinterpret_cast<uintptr_t>(e->du) & 15) == 0) &&
+                  (!p->src.pa || (reinterpret_cast<uintptr_t>(p->src.pa) & 15) == 0) &&
+                  (!p->src.pb || (reinterpret_cast<uintptr_t>(p->src.pb) & 15) == 0) &&
+                  (!e->center || (reinterpret_cast<uintptr_t>(e->center) & 15) == 0) &&
+                  (reinterpret_cast<uintptr_t>(p->argidx) & 3) == 0;
+  if (v4) {
+    const unsigned ppb = ET / (unsigned)(p->C / 4);
+    int64_t blocks = hdn_cdiv(M_in, (int64_t)ppb);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    maxpool_bwd_idx_v4<<<(unsigned)blocks, ET, sm, ST>>>(*p, *e, (unsigned)M_in);
+  } else if (p->kind == 0 && p->argidx) maxpool_bwd_idx<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
   else if (p->kind == 0) maxpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
   else avgpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
   HDN_CHECK_LAUNCH("pool_bwd");

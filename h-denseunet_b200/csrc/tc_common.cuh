@@ -196,6 +196,68 @@ __device__ __forceinline__ void xform_chunk(const float* rawc, int RS, const int
     }
   }
 }
+// Two-source form (A = f0(src0) + f1(src1): the Add in front of a convolution, merge.py:207-211): same mapping, the
+// (a, b) of both sources in registers, four 16-byte reads in flight per pixel.  Zero padding depends on the virtual
+// pixel alone, so vq0[q] < 0 exactly when vq1[q] < 0.
+template <int MODE>
+__device__ __forceinline__ void xform_apply(float4& va, float4& vb, const float4& a0, const float4& a1, const float4& b0,
+                                            const float4& b1) {
+  if (MODE == 1) {
+    va.x = fmaxf(fmaf(a0.x, va.x, b0.x), 0.f); va.y = fmaxf(fmaf(a0.y, va.y, b0.y), 0.f);
+    va.z = fmaxf(fmaf(a0.z, va.z, b0.z), 0.f); va.w = fmaxf(fmaf(a0.w, va.w, b0.w), 0.f);
+    vb.x = fmaxf(fmaf(a1.x, vb.x, b1.x), 0.f); vb.y = fmaxf(fmaf(a1.y, vb.y, b1.y), 0.f);
+    vb.z = fmaxf(fmaf(a1.z, vb.z, b1.z), 0.f); vb.w = fmaxf(fmaf(a1.w, vb.w, b1.w), 0.f);
+  }
+}
+template <int M0, int M1, bool SPLIT>
+__device__ __forceinline__ void xform_chunk2(const float* raw0c, const float* raw1c, int RS, const int* vq0, const int* vq1,
+                                             int P, int q0, int qstep, const float* a80, const float* b80, const float* a81,
+                                             const float* b81, bool cvalid, uint8_t* dchunk, uint8_t* dtail) {
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 p0 = one, p1 = one, r0 = zero, r1 = zero, s0 = one, s1 = one, t0 = zero, t1 = zero;
+  if (M0 == 1) {
+    p0 = *reinterpret_cast<const float4*>(a80); p1 = *reinterpret_cast<const float4*>(a80 + 4);
+    r0 = *reinterpret_cast<const float4*>(b80); r1 = *reinterpret_cast<const float4*>(b80 + 4);
+  }
+  if (M1 == 1) {
+    s0 = *reinterpret_cast<const float4*>(a81); s1 = *reinterpret_cast<const float4*>(a81 + 4);
+    t0 = *reinterpret_cast<const float4*>(b81); t1 = *reinterpret_cast<const float4*>(b81 + 4);
+  }
+  for (int q = q0; q < P; q += qstep) {
+    const int sq0 = vq0[q], sq1 = vq1[q];
+    const float* rowa = raw0c + max(sq0, 0) * RS;
+    const float* rowb = raw1c + max(sq1, 0) * RS;
+    float4 xa0 = *reinterpret_cast<const float4*>(rowa), xa1 = *reinterpret_cast<const float4*>(rowa + 4);
+    float4 xb0 = *reinterpret_cast<const float4*>(rowb), xb1 = *reinterpret_cast<const float4*>(rowb + 4);
+    xform_apply<M0>(xa0, xa1, p0, p1, r0, r1);
+    xform_apply<M1>(xb0, xb1, s0, s1, t0, t1);
+    xa0.x += xb0.x; xa0.y += xb0.y; xa0.z += xb0.z; xa0.w += xb0.w;
+    xa1.x += xb1.x; xa1.y += xb1.y; xa1.z += xb1.z; xa1.w += xb1.w;
+    uint4 o, t;
+    xform_px<0, SPLIT>(xa0, xa1, one, one, zero, zero, sq0 >= 0 && sq1 >= 0 && cvalid, o, t);
+    *reinterpret_cast<uint4*>(dchunk + (uint32_t)q * 16u) = o;
+    if (SPLIT) *reinterpret_cast<uint4*>(dtail + (uint32_t)q * 16u) = t;
+  }
+}
+// the two-source shapes the networks contain: (BN+ReLU, BN+ReLU) = fianl_conv (hybridnet.py:414-415) and
+// (plain, BN+ReLU) = the skip-add decoder (denseunet.py:190-209).  Returns false for any other combination.
+__device__ __forceinline__ bool xform_chunk2_any(int m0, int m1, bool split, const float* raw0c, const float* raw1c, int RS,
+                                                 const int* vq0, const int* vq1, int P, int q0, int qstep, const float* a80,
+                                                 const float* b80, const float* a81, const float* b81, bool cvalid,
+                                                 uint8_t* dchunk, uint8_t* dtail) {
+  if (m0 == 1 && m1 == 1) {
+    if (split) xform_chunk2<1, 1, true>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    else       xform_chunk2<1, 1, false>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    return true;
+  }
+  if (m0 == 0 && m1 == 1) {
+    if (split) xform_chunk2<0, 1, true>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    else       xform_chunk2<0, 1, false>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    return true;
+  }
+  return false;
+}
+
 // dispatch on the two runtime-uniform switches
 __device__ __forceinline__ void xform_chunk_any(int mode, bool split, const float* rawc, int RS, const int* vq, int P, int q0,
                                                 int qstep, const float* a8, const float* b8, bool cvalid, uint8_t* dchunk,

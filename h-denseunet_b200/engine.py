@@ -21,8 +21,13 @@ import torch
 from . import _lib
 
 
-# Net(precision=...) -> hdn_conv.precision of the convolutions the tcgen05 path takes (include/hdn.h)
-TC_PRECISION = {"bf16": 1, "bf16x3": 2}
+# Net(precision=...) -> hdn_conv.precision per pass (fprop, dgrad, wgrad) of the convolutions the tcgen05 path takes
+# (include/hdn.h: 1 = bf16 operands, 2 = bf16x3 head + tail split; fp32 accumulation in both).
+#   "bf16"   : everything on rounded-to-bf16 operands (fastest; ~1.5e-2 from the fp32 oracle after 200+ layers)
+#   "bf16x3" : everything split (fp32-grade results in all three passes)
+#   "mixed"  : the activation path -- fprop and dgrad, whose rounding errors compound layer after layer -- split, the
+#              weight gradients (a leaf: their rounding error stays in that one tensor, ~3e-3) on plain bf16 operands
+TC_PRECISION = {"bf16": (1, 1, 1), "bf16x3": (2, 2, 2), "mixed": (2, 2, 1)}
 
 
 # ------------------------------------------------------------------------- descriptors
@@ -206,10 +211,14 @@ class CudaBackend(object):
 
     # -- ops
     def conv_tc_supported(self, d, which):
-        return bool(self.lib.hdn_conv_tc_supported(C.byref(self._conv(d)), which))
+        c = self._conv(d)
+        c.precision = d.precision          # the cached struct may carry another pass's precision
+        return bool(self.lib.hdn_conv_tc_supported(C.byref(c), which))
 
     def conv_tc_workspace(self, d, which):
-        return int(self.lib.hdn_conv_tc_workspace(C.byref(self._conv(d)), which))
+        c = self._conv(d)
+        c.precision = d.precision
+        return int(self.lib.hdn_conv_tc_workspace(C.byref(c), which))
 
     def conv_fprop(self, d):
         self._cur = d.name
@@ -528,9 +537,8 @@ class ConvOp(object):
                              drop_keep=1.0 - self.drop_rate, drop_seed=0, precision=0)
         self.prec = [0, 0, 0]
         if net.precision in TC_PRECISION:
-            # tensor-core path: 1 = bf16 operands, 2 = bf16x3 (head + tail split, fp32-grade results); fp32 accumulation
-            self.desc.precision = TC_PRECISION[net.precision]
             for i in range(3):
+                self.desc.precision = TC_PRECISION[net.precision][i]
                 self.prec[i] = self.desc.precision if net.be.conv_tc_supported(self.desc, i) else 0
                 if self.prec[i]:
                     net.ws_need = max(net.ws_need, net.be.conv_tc_workspace(self.desc, i))

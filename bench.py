@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--cols", type=int, default=48)
     ap.add_argument("--batch", type=int, default=2, help="slabs per GPU (north star: 2)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "mixed", "fp32"],
+    ap.add_argument("--precision", default="mixed", choices=["bf16", "bf16x3", "mixed", "fp32"],
                     help="bf16: tcgen05, operands rounded to bf16; bf16x3: tcgen05, operands split into bf16 head + tail "
                          "(3 MMAs per step, fp32-grade results); mixed: fprop + dgrad bf16x3, wgrad bf16; fp32: FMA parity path")
     ap.add_argument("--no-dropout", action="store_true")

@@ -974,14 +974,14 @@ __global__ void __launch_bounds__(256) zero_window_kernel(hdn_tensor t, long lon
 
 }  // namespace
 
-// HDN_TC_FASTX=0/1/2 selects the operand-transform form of the tcgen05 kernels (read once per process; default 1,
-// validated on B200 in round 1: profiles/r01b_*)
+// HDN_TC_FASTX=0/1/2 selects the operand-transform form of the tcgen05 kernels (read once per process; default 2,
+// validated on B200 in round 1: profiles/r01b_*, r01c_*)
 int hdn_tc_fastx() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("HDN_TC_FASTX");
-    v = e ? atoi(e) : 1;                  // 0 generic, 1 single-source warp-per-chunk form, 2 also the two-source form
-    if (v < 0 || v > 2) v = 1;
+    v = e ? atoi(e) : 2;                  // 0 generic, 1 single-source warp-per-chunk form, 2 also the two-source form
+    if (v < 0 || v > 2) v = 2;
   }
   return v;
 }

@@ -497,12 +497,13 @@ __global__ void __launch_bounds__(ET) window_fin_kernel(float* __restrict__ scor
 
 #define ST ((cudaStream_t)stream)
 
-// HDN_POOL_FAST=0/1: four-channels-per-thread max-pool backward (read once per process)
+// HDN_POOL_FAST=0/1: four-channels-per-thread max-pool backward (read once per process; default 1, validated on B200 in
+// round 1: profiles/r01c_*)
 static int hdn_pool_fast() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("HDN_POOL_FAST");
-    v = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+    v = e ? (atoi(e) != 0 ? 1 : 0) : 1;
   }
   return v;
 }

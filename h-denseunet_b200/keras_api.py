@@ -55,7 +55,7 @@ class Model(object):
                  backend=None, device=None, dropout=False):
         self.kind, self.name, self.mode = kind, name, models.Mode(mode)
         self.b, self.size, self.cols, self.skip = int(batch), int(size), cols, skip
-        self.precision = precision or os.environ.get("HDN_PRECISION", "bf16")
+        self.precision = precision or os.environ.get("HDN_PRECISION", "mixed")
         self.backend = backend
         self.device = device
         self.dropout = dropout

@@ -168,6 +168,7 @@ def hybrid_net(net, B, S, H, W, mode):
     logits = net.conv("2d3dclassifer", [a], 3, (1, 1, 1))
     net.outputs["logits"] = logits
     net.outputs["logits2d"] = logits2d
+    net.outputs["feature2d"] = feat2d
     return logits
 
 

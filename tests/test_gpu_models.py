@@ -287,3 +287,21 @@ def test_hybrid_train_step_parity_tensor_cores(cuda_dev, precision):
         de = orc.dice((pe[..., cls] > thr) & keep, (lab[..., 0] == cls) & keep)
         do = orc.dice((po[..., cls] > thr) & keep, (lab[..., 0] == cls) & keep)
         assert round(de, 4) == round(do, 4)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HDN_TEST_PENDING") != "1",
+                    reason="written after round 1's GPU minutes were spent: first B200 run pending (HDN_TEST_PENDING=1 enables); "
+                           "the same host logic runs on the CPU reference backend in tests/test_inference_cpu.py")
+def test_sliding_window_slice_reuse_matches_full_evaluation(cuda_dev):
+    """inference.SliceReuse on the CUDA engine: bit-identical to evaluating every window in full."""
+    a = Args(b=1, input_size=32, input_cols=8)
+    m = hdn.dense_rnn_net(a, precision="fp32")
+    perturb_params(m)
+    rng = np.random.default_rng(11)
+    vol = rng.normal(0, 60, (32, 32, 23)).astype(np.float32)
+    mini, maxi = np.array([0, 0, 4]), np.array([31, 31, 15])
+    st0, st1 = {}, {}
+    s1, s2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a, reuse_2d=False, stats=st0)
+    r1, r2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a, reuse_2d=True, stats=st1)
+    assert np.array_equal(s1, r1) and np.array_equal(s2, r2)
+    assert st1["slices_2d"] <= 0.6 * st0["slices_2d"]

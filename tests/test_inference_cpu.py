@@ -120,3 +120,34 @@ def test_predict_tumor_inwindow_two_ranks_gloo():
     assert out[0]["n_windows"] > 0 and out[1]["n_windows"] > 0
     assert out[0]["e1"] < 1e-4 and out[0]["e2"] < 1e-4                      # sharded result == the reference loop
     assert np.array_equal(out[0]["s1"], out[1]["s1"]) and np.array_equal(out[0]["s2"], out[1]["s2"])
+
+
+def test_new_slices_of_a_moved_window():
+    from h_denseunet_b200.inference import new_slices
+    assert new_slices(8, 2) == [0, 5, 6, 7]          # stride 2: two new interior slices + the two edges
+    assert new_slices(8, 1) == [0, 6, 7]             # clamped tail window one slice further
+    assert new_slices(12, 3) == [0, 8, 9, 10, 11]
+
+
+def test_slice_reuse_is_bit_identical_and_halves_the_2d_work():
+    """with the 2-D per-slice results reused across the 75 %-overlapping windows the output is
+    unchanged (inference-mode BN: slices are independent) and a window after the first costs step + 2 = 4 slice
+    evaluations of the 2-D network instead of 8."""
+    _setup_paths()
+    import h_denseunet_b200 as hdn
+    from h_denseunet_b200.inference import window_starts
+    torch.set_num_threads(4)
+    m, a, vol, mini, maxi = _model_and_volume()
+    vol = np.concatenate([vol, vol[:, :, :3]], axis=2)            # z = 23: the tail window is clamped (odd step of 1)
+    st0, st1 = {}, {}
+    s1, s2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a, reuse_2d=False, stats=st0)
+    r1, r2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a, reuse_2d=True, stats=st1)
+    assert np.array_equal(s1, r1) and np.array_equal(s2, r2)
+    starts = window_starts(23, 4, 15, 8)
+    steps = [b - a_ for a_, b in zip(starts, starts[1:])]
+    assert st0["windows"] == st1["windows"] == len(starts)
+    assert st0["slices_2d"] == 8 * len(starts)
+    assert st1["slices_2d"] == 8 + sum(d + 2 for d in steps)
+    assert st1["slices_2d"] <= 0.6 * st0["slices_2d"]
+    o1, o2 = _oracle_result(m, vol, mini, maxi)
+    assert np.abs(r1 - o1).max() < 1e-4 and np.abs(r2 - o2).max() < 1e-4

@@ -232,7 +232,7 @@ def run_gpu(a):
     # end-to-end arm: host numpy in, loss out, every step
     m.train_on_batch(vol, lab)
     ms_e2e, loss_e2e = timed(lambda: m.train_on_batch(vol, lab), a.steps, dist, dev)
-    h2d = int(vol.nbytes + lab.astype(np.float32).nbytes)
+    h2d = int(m.h2d_bytes)          # bytes Model.train_on_batch copied host -> device this step (fp32 volume + int16 label map)
 
     slabs_step = a.batch * world * (a.size * a.size * a.cols) / float(FULL_VOXELS)
     value = slabs_step / (ms * 1e-3)

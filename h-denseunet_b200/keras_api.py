@@ -129,41 +129,51 @@ class Model(object):
         return x.nbytes
 
     def _h2d(self, x, dst, three_d):
-        """host (reference layout) -> device NDHWC through a pinned staging buffer."""
-        key = (x.shape, dst.device)
+        """host (reference layout) -> device NDHWC through a pinned staging buffer.  The staging buffers keep the
+        host array's dtype (float32 volumes, int16 label maps -- half the bytes over PCIe and no host-side cast);
+        the conversion to the fp32 device tensor happens on the device, inside the layout-changing copy."""
+        tdt = torch.int16 if x.dtype == np.int16 else torch.float32
+        if tdt == torch.float32 and x.dtype != np.float32:
+            x = np.asarray(x, dtype=np.float32)
+        key = (x.shape, dst.device, tdt)
         st = self._staging.get(key)
         if st is None:
             pin = dst.device.type == "cuda"
-            st = (torch.empty(x.shape, dtype=torch.float32, pin_memory=pin),
-                  torch.empty(x.shape, dtype=torch.float32, device=dst.device) if three_d else None)
+            need_dev = three_d or tdt != torch.float32
+            st = (torch.empty(x.shape, dtype=tdt, pin_memory=pin),
+                  torch.empty(x.shape, dtype=tdt, device=dst.device) if need_dev else None)
             self._staging[key] = st
         ev = self._staging_ev.get(key)
         if ev is not None:
             ev.synchronize()          # the previous async copy out of this pinned buffer must have finished
-        st[0].copy_(torch.from_numpy(x))
+        st[0].copy_(torch.from_numpy(np.ascontiguousarray(x)))
         if three_d:    # (N,H,W,S,C) -> (N,S,H,W,C)
             st[1].copy_(st[0], non_blocking=True)
             dst.copy_(st[1].permute(0, 3, 1, 2, 4))
         elif dst.shape[-1] != x.shape[-1] and dst.dim() == 5 and x.ndim == 4:
             # 2-D input (N,H,W,3) into the 4-channel padded buffer (N,1,H,W,4); channel 3 stays zero
             dst[:, 0, :, :, :x.shape[-1]].copy_(st[0], non_blocking=True)
+        elif st[1] is not None:
+            st[1].copy_(st[0], non_blocking=True)
+            dst.view(x.shape).copy_(st[1])
         else:
             dst.view(x.shape).copy_(st[0], non_blocking=True)
         if dst.device.type == "cuda":
             if ev is None:
                 ev = self._staging_ev[key] = torch.cuda.Event()
             ev.record()
+        return x.nbytes
 
     def _labels(self, net, y):
-        y = np.asarray(y, dtype=np.float32)
+        y = np.asarray(y)
+        if y.dtype != np.int16:       # the reference feeds int16 label maps (train_hybrid.py:127-132); anything else as float
+            y = np.asarray(y, dtype=np.float32)
         lab = net.loss.labels
         if self.kind == "unet2d":
             y = y.reshape(self.b, self.size, self.size)
-            self._h2d(y, lab, three_d=False)
-        else:
-            y = y.reshape(self.b, self.size, self.size, self.cols, 1)
-            self._h2d(y, lab.view(lab.shape + (1,)), three_d=True)
-        return y.nbytes
+            return self._h2d(y, lab, three_d=False)
+        y = y.reshape(self.b, self.size, self.size, self.cols, 1)
+        return self._h2d(y, lab.view(lab.shape + (1,)), three_d=True)
 
     def train_on_batch(self, x, y, **kwargs):
         if self.optimizer is None:

@@ -10,7 +10,7 @@ step() { echo "$1 rc=$2 t=$(el)s" >> gpurun_out/status_c.txt; }
 export HDN_TC_FASTX=2 HDN_POOL_FAST=1
 PT="python -m pytest -q --tb=line -p no:cacheprovider"
 timeout 200 $PT tests -m gpu > gpurun_out/c1_full_fastx2_pool1.txt 2>&1; step c1_full $?
-timeout 120 python scripts/grad_errors.py mixed bf16x3 bf16 > gpurun_out/c2_grad_errors.txt 2> gpurun_out/c2_err.txt; step c2_grad_errors $?
+timeout 120 python tests/grad_errors.py mixed bf16x3 bf16 > gpurun_out/c2_grad_errors.txt 2> gpurun_out/c2_err.txt; step c2_grad_errors $?
 timeout 120 python bench.py --steps 2 --warmup 3 --no-cpu --precision mixed > gpurun_out/c3_bench_mixed.json 2> gpurun_out/c3_err.txt; step c3_bench_mixed $?
 timeout 120 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/c4_bench_bf16.json 2> gpurun_out/c4_err.txt; step c4_bench_bf16 $?
 HDN_POOL_FAST=0 timeout 60 $PT tests/test_gpu_tc.py -k "two_src or skip" > gpurun_out/c5_two_src_only.txt 2>&1; step c5_two_src $?

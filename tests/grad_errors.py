@@ -1,5 +1,6 @@
 """Parity numbers of one hybrid (end2end) train step at 64x64x8 for a given precision, against the fp32 / fp64 oracle:
-logits rel-L2, loss, and the per-tensor gradient rel-L2 distribution (GPU).  python scripts/grad_errors.py mixed bf16x3 ..."""
+logits rel-L2, loss, and the per-tensor gradient rel-L2 distribution (GPU).  A measurement tool of the test suite (it
+uses the oracle as the checker): python tests/grad_errors.py mixed bf16x3 bf16 -> profiles/r01c_grad_errors.txt"""
 import json
 import os
 import sys
@@ -7,6 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

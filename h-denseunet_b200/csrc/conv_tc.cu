@@ -45,14 +45,12 @@ constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA
 constexpr int NPROD = 256;        // producer threads
 constexpr int NSA = 2;        // bf16 A-operand stages
 constexpr int NSB_MAX = 16;   // weight-block ring depth upper bound
-constexpr int NRAW_MAX = 4;   // raw fp32 patch ring depth upper bound
-constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs < NRAW_MAX tiles ahead of the transform)
+constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs at most 3 stages ahead of the transform)
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
 constexpr int RB = 32;        // dgrad epilogue: rows fetched ahead per lane
 constexpr int MAXC0 = 14;     // copies per producer thread and stage, source 0 (4-tap stems' dgrad: 19x11 px x 16 quads / 256 threads)
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
-constexpr int TU = 3;         // transform: pixel groups looked up / fetched ahead per warp
 
 struct TcParams {
   int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
@@ -176,31 +174,6 @@ __device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q,
   if (even) { o.x = p00; o.y = p01; o.z = x0; o.w = x1; }     // chunk i      = [own quad A | partner quad A]
   else      { o.x = x0; o.y = x1; o.z = p10; o.w = p11; }     // chunk 4 + i  = [partner quad B | own quad B]
   if (qok) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
-}
-
-// Column sums over the 32 rows (lanes) of a warp for 16 columns held one row per lane, by recursive halving:
-// 16 shuffles instead of 16 x 5.  Every lane returns the total of column (lane >> 1).  v is clobbered.
-__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float send = (lane & 16) ? v[i] : v[i + 8], keep = (lane & 16) ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = (lane & 8) ? v[i] : v[i + 4], keep = (lane & 8) ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = (lane & 4) ? v[i] : v[i + 2], keep = (lane & 4) ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  {
-    const float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {

@@ -21,6 +21,17 @@
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
 
+// -DHDN_TC_TIMING: per-role wait/work cycle counters of CTA 0, printed at kernel end (development aid, as in conv_tc.cu)
+#ifdef HDN_TC_TIMING
+#define WT_DECL(n) long long n = 0
+#define WT_BEGIN long long wt__0 = clock64()
+#define WT_ADD(n) do { long long wt__1 = clock64(); n += wt__1 - wt__0; wt__0 = wt__1; } while (0)
+#else
+#define WT_DECL(n)
+#define WT_BEGIN
+#define WT_ADD(n)
+#endif
+
 int hdn_tc_stem(const hdn_conv* c);   // conv_tc.cu
 int hdn_tc_fastx();                   // conv_tc.cu
 
@@ -321,14 +332,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (++slot_is == p.nraw) slot_is = 0;
       }
+      WT_DECL(t_cp); WT_DECL(t_bar); WT_DECL(t_issue); WT_DECL(t_empty); WT_DECL(t_xa); WT_DECL(t_xb); WT_DECL(n_sub);
       while (!tr.done) {
+        WT_BEGIN;
         if (p.nraw == 2) asm volatile("cp.async.wait_group 0;" ::: "memory");
         else asm volatile("cp.async.wait_group 1;" ::: "memory");
+        WT_ADD(t_cp);
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        WT_ADD(t_bar);
         if (!is.done) { issue(is, slot_is); advance(is); }
         asm volatile("cp.async.commit_group;" ::: "memory");
         if (++slot_is == p.nraw) slot_is = 0;
+        WT_ADD(t_issue);
         if (tr.u == 0) { produced = true; tc::mbar_wait(&empty[st], ph ^ 1); }
+        WT_ADD(t_empty);
+#ifdef HDN_TC_TIMING
+        const bool wt_is_a = tr.u < nA;
+#endif
         const int* tab = tabs + (tr.seq % NTW) * p.tab_ints;
         const uint8_t* raw = sRaw + (size_t)slot_tr * p.raw_bytes;
         if (tr.u < nA) {
@@ -454,7 +474,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         }
         if (++slot_tr == p.nraw) slot_tr = 0;
         advance(tr);
+#ifdef HDN_TC_TIMING
+        if (wt_is_a) WT_ADD(t_xa); else WT_ADD(t_xb);
+        ++n_sub;
+#endif
       }
+#ifdef HDN_TC_TIMING
+      if (blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 255) && n_sub > 0)
+        printf("[wgrad prod t%d] sub-stages %lld (nA %d nB %d)  cp_wait %lld  bar %lld  issue %lld  empty %lld  xform_A %lld  xform_dY %lld (cycles/sub-stage)\n",
+               tid, n_sub, nA, nB, t_cp / n_sub, t_bar / n_sub, t_issue / n_sub, t_empty / n_sub, t_xa / n_sub, t_xb / n_sub);
+#endif
     } else {
     // ---- direct path (space-to-depth stems)
     for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
@@ -599,12 +628,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
       const int t20 = tap0 % taps_hw;
       const int twc0 = (p.G == 1) ? 0 : (t20 % p.kw);
       const uint32_t tap_units0 = (uint32_t)((t20 / p.kw - gth0) * p.PW + (t20 % p.kw - gtw0));
+      WT_DECL(t_full); WT_DECL(t_mma); WT_DECL(n_tile);
       for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
         int n_img, d0, h0, w0;
         long long m0;
         if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
+        WT_BEGIN;
         tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
+        WT_ADD(t_full);
         // lean issue loop (one serial thread): descriptors are advanced by integer adds on the 14-bit start-address field
         const uint64_t ad0 = adesc_hi | (uint64_t)((tc::smem_u32(sA + st * A_BYTES) >> 4) & 0x3FFF);
         const uint64_t bd0 = bdesc_hi | (uint64_t)((tc::smem_u32(sB + st * B_BYTES) >> 4) & 0x3FFF);
@@ -621,8 +653,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         acc = 1;
         tc::umma_commit(&empty[st]);
         if (++st == NS) { st = 0; ph ^= 1; }
+        WT_ADD(t_mma);
+#ifdef HDN_TC_TIMING
+        ++n_tile;
+#endif
       }
       tc::umma_commit(acc_full);
+#ifdef HDN_TC_TIMING
+      if (blockIdx.x == 0 && blockIdx.y == 0 && n_tile > 0)
+        printf("[wgrad mma] tiles %lld  full_wait %lld  issue %lld (cycles/tile)  G %d BNe %d\n", n_tile, t_full / n_tile, t_mma / n_tile, p.G, p.BNe);
+#endif
     }
   }
 

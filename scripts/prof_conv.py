@@ -1,5 +1,7 @@
 """Time (CUDA events) one convolution through the C-ABI at a realistic size; used under ncu for the
-per-kernel captures kept in profiles/.  python scripts/prof_conv.py <case> <pass> [reps]"""
+per-kernel captures kept in profiles/.  python scripts/prof_conv.py <case> <pass> [reps] [precision 1|2]
+(precision 1 = bf16 operands, 2 = bf16x3; a library built with HDN_NVCC_EXTRA=-DHDN_TC_TIMING also prints the per-role
+wait / work cycle counters of CTA 0)"""
 import os
 import sys
 import time
@@ -28,19 +30,20 @@ CASES = {
 def main():
     name, which = sys.argv[1], sys.argv[2]
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+    prec = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     dev = torch.device("cuda:0")
-    c = Case(dev, **CASES[name])
+    c = Case(dev, tc=prec, **CASES[name])
     op, d, net = c.op, c.op.desc, c.net
     flops = 2.0 * d.out.M * d.Cin * d.Cout * d.k[0] * d.k[1] * d.k[2]
     if which == "fprop":
         fn = lambda: (op._set_prec(0), net.be.conv_fprop(d))
-        op.prec = [1, 1, 1]
+        op.prec = [prec] * 3
     elif which == "wgrad":
-        op.prec = [1, 1, 1]
+        op.prec = [prec] * 3
         fn = lambda: (op._set_prec(2), net.be.conv_wgrad(d, op.w.g, None))
     else:
         from h_denseunet_b200.engine import EpiDesc
-        op.prec = [1, 1, 1]
+        op.prec = [prec] * 3
         epis = []
         for s, b in zip(op.srcs, c.src_bufs):
             v = s.act.view

@@ -184,8 +184,26 @@ def profile_step(model, net, steps):
             o[0] += t
             o[1] += flops
             o[2] += 1
+    # device idle time between consecutive C-ABI calls (end event of call i -> start event of call i+1): tells a
+    # launch-bound step (host cannot keep the queue full) from a kernel-bound one.  Diagnostic only: never fatal.
+    gaps = {"total_ms": None}
+    try:
+        total, worst = 0.0, {}
+        prof = be.prof
+        for i in range(len(prof) - 1):
+            g = prof[i][3].elapsed_time(prof[i + 1][2])
+            if g > 0:
+                total += g
+                w = worst.setdefault(prof[i + 1][0], [0.0, 0])
+                w[0] += g
+                w[1] += 1
+        gaps = {"total_ms": round(total / max(steps, 1), 3), "calls": len(prof) // max(steps, 1),
+                "before": {k: {"ms": round(v[0] / max(steps, 1), 3), "n": v[1] // max(steps, 1)}
+                           for k, v in sorted(worst.items(), key=lambda kv: -kv[1][0])[:6]}}
+    except Exception as ex:                                   # noqa: BLE001
+        gaps = {"total_ms": None, "error": str(ex)[:120]}
     be.prof = None
-    return agg, ops
+    return agg, ops, gaps
 
 
 def run_gpu(a):
@@ -256,7 +274,7 @@ def run_gpu(a):
 
     # roofline of the dominant kernel class, measured live with CUDA events (one extra instrumented step; every rank
     # takes part because the data-parallel exchange inside the step is collective)
-    agg, ops = profile_step(m, net, a.profile_steps)
+    agg, ops, gaps = profile_step(m, net, a.profile_steps)
     if rank == 0:
         tot = sum(v[0] for v in agg.values())
         # the dominant kernel = the single most expensive convolution launch of the step (class + layer name)
@@ -287,6 +305,7 @@ def run_gpu(a):
         line["kernel_classes"] = {kk: {"ms": round(v[0] / a.profile_steps, 3), "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 2),
                                         "launches": v[2] // a.profile_steps}
                                   for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+        line["launch_gaps"] = gaps
         # CPU baseline on this box's host cores, bounded sample
         if not a.no_cpu:
             threads = min(os.cpu_count() or 1, a.cpu_threads)   # oneDNN convolutions of this size stop scaling past ~32 threads

@@ -72,7 +72,7 @@ class ClockSampler(object):
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -80,13 +80,17 @@ class ClockSampler(object):
                 mx.append(float(r[1]))
             except (ValueError, IndexError):
                 continue
+            try:
+                pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                pass
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sm_min_mhz": float(min(sm)), "power_w_max": float(max(pw)) if pw else None}
 
 
 # --------------------------------------------------------------------------------- CPU arm

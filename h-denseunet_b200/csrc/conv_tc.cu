@@ -69,6 +69,7 @@ struct TcParams {
   hdn_src src[2];             // A operand sources
   const __nv_bfloat16* wpack;
   int mode;                   // 0 fprop, 1 dgrad
+  int l2pf;                   // 1: raw patch copies carry the L2::256B prefetch hint (HDN_TC_L2PF, experiment)
   int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
   int pd_lo, ph_lo, pw_lo;    // patch origin = tile origin - p*_lo (padding in front of tap 0)
@@ -147,6 +148,10 @@ __device__ __forceinline__ float4 prologue4(float4 x, float4 a, float4 b, int re
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// same copy with the L2 prefetch hint: the first 16 bytes of a pixel's 256-byte channel sliver pull the whole sliver into L2
+__device__ __forceinline__ void cp_async16_l2(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait(int n) {     // n groups may remain in flight
@@ -308,10 +313,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         {
           const float* base = slab_base(it, 0) + c0;
           uint8_t* rs = raw + p.raw_off[0] + d0;
-          if (cok) {
+          if (cok && !p.l2pf) {
 #pragma unroll
             for (int j = 0; j < MAXC0; ++j)
               if (goff0[j] >= 0) cp_async16(rs + j * dj, base + goff0[j]);
+          } else if (cok) {
+#pragma unroll
+            for (int j = 0; j < MAXC0; ++j)
+              if (goff0[j] >= 0) cp_async16_l2(rs + j * dj, base + goff0[j]);
           }
         }
         if (p.nsrc > 1) {
@@ -959,6 +968,16 @@ int hdn_tc_fastx() {
   return v;
 }
 
+// HDN_TC_L2PF=1: experiment switch, see TcParams::l2pf (default 0)
+int hdn_tc_l2pf() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDN_TC_L2PF");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v;
+}
+
 namespace {
 
 struct TcPlan {
@@ -1137,6 +1156,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.mode = mode;
   p.split = nsplit == 2 ? 1 : 0;
   p.fastx = hdn_tc_fastx();
+  p.l2pf = hdn_tc_l2pf();
   if (mode == 0) {
     p.nsrc = c->nsrc;
     p.src[0] = c->src[0];

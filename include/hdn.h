@@ -17,6 +17,10 @@
  *     element (n,d,h,w,c) lives at  base[(((n*D+d)*H+h)*W+w)*ldc + coff + c].
  *   - conv weights are [kd][kh][kw][Cin][Cout] fp32 (Keras HWIO / DHWIO with the slice axis
  *     moved first).
+ *   - process-wide switches read once from the environment (defaults are the validated forms):
+ *       HDN_TC_FASTX=0|1|2  operand-transform form of the tcgen05 kernels (default 2)
+ *       HDN_POOL_FAST=0|1   vector max-pool backward (default 1)
+ *       HDN_TC_L2PF=0|1     L2::256B prefetch hint on the raw patch copies (default 0, experiment)
  */
 #ifndef HDN_H_
 #define HDN_H_

@@ -41,6 +41,14 @@
 
 namespace {
 
+// -DHDN_TC_X3FOLD compiles the folded bf16x3 issue scheme in (experiment, see TcParams::fold); without it the code is
+// absent and the kernel is the one validated on B200 in round 1
+#ifdef HDN_TC_X3FOLD
+constexpr bool kFold = true;
+#else
+constexpr bool kFold = false;
+#endif
+
 constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
 constexpr int NPROD = 256;        // producer threads
 constexpr int NSA = 2;        // bf16 A-operand stages
@@ -69,6 +77,8 @@ struct TcParams {
   hdn_src src[2];             // A operand sources
   const __nv_bfloat16* wpack;
   int mode;                   // 0 fprop, 1 dgrad
+  int fold;                   // bf16x3 with BN <= 128 (HDN_TC_X3FOLD, experiment): weight chunks laid out [head | tail] along N, the
+                              //   accumulator is 2*BN columns wide, A_hi x [B_hi | B_lo] is ONE MMA (+ A_lo x B_hi): 2 MMAs per step
   int l2pf;                   // 1: raw patch copies carry the L2::256B prefetch hint (HDN_TC_L2PF, experiment)
   int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
@@ -542,6 +552,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint64_t adesc_hi = tc::make_smem_desc(0, lbo_a, sbo_a), bdesc_hi = tc::make_smem_desc(0, lbo_b, sbo_b);
       const uint64_t kstep_a = (uint64_t)((2u * lbo_a) >> 4), kstep_b = (uint64_t)((2u * lbo_b) >> 4);
       const uint64_t tail_a = (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_a) >> 4), tail_b = (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_b) >> 4);
+      // folded bf16x3: chunk stride of the [head | tail] weight block is 2*BN rows; N = 2*BN for A_hi, N = BN for A_lo
+      const uint32_t idesc_f2 = tc::make_idesc_bf16(128, 2 * p.BN, 0, 0);
+      const uint64_t bdesc_hi_f = tc::make_smem_desc(0, 2u * lbo_b, sbo_b), kstep_b_f = (uint64_t)((4u * lbo_b) >> 4);
       TT_DECL(t_acc); TT_DECL(t_afull); TT_DECL(t_bfull); TT_DECL(t_mma); TT_DECL(n_st);
       while (!it.done) {
         TT_BEGIN;
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int ab = cur_seq & 1;
           tc::mbar_wait(&acc_empty[ab], ((uint32_t)(cur_seq >> 1) & 1u) ^ 1u);
           tc::tc_fence_after();
-          tmem_d = tmem_base + (uint32_t)(ab * p.BN);
+          tmem_d = tmem_base + (uint32_t)(ab * ((kFold && p.fold) ? 2 * p.BN : p.BN));
           acc = 0;
         }
         const int cv = min(p.CK, p.K - it.kb * p.CK);
@@ -576,6 +589,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
             if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
             if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
+          } else if (kFold && p.fold) {
+            const uint64_t bdf = bdesc_hi_f | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
+            for (int s = 0; s < nk; ++s) {
+              const uint64_t ah = ad + (uint64_t)s * kstep_a, bf = bdf + (uint64_t)s * kstep_b_f;
+              tc::umma_bf16(tmem_d, ah, bf, idesc_f2, acc);            // A_hi x [B_hi | B_lo] -> columns [0, 2BN)
+              tc::umma_bf16(tmem_d, ah + tail_a, bf, idesc, 1u);       // A_lo x B_hi         -> columns [0, BN)
+              acc = 1;
+            }
           } else {
             // bf16x3: tails first (small terms), head x head last; tail operands sit CK/8 chunks behind the heads
             for (int s = 0; s < nk; ++s) {
@@ -656,7 +677,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #ifdef HDN_TC_TIMING
       te_wait += clock64() - te0; te0 = clock64();
 #endif
-      const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * p.BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * ((kFold && p.fold) ? 2 * p.BN : p.BN));
+      // accumulator columns [col, col+16) of this lane's row; folded bf16x3 adds the A_hi x B_lo half BN columns further
+      auto ld_acc = [&](int col, float* dst) {
+        tc::tmem_ld16(taddr + (uint32_t)col, dst);
+        if (kFold && p.fold) {
+          float w2[16];
+          tc::tmem_ld16(taddr + (uint32_t)(p.BN + col), w2);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dst[i] += w2[i];
+        }
+      };
 
       if (p.mode == 0) {
         // Transposed epilogue: the warp's 32 x 32 accumulator block goes through shared memory so that lane = output
@@ -672,8 +703,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int cb = 0; cb < p.BN; cb += 32) {
           const int ncols = min(32, p.BN - cb);
           float v2[16];
-          tc::tmem_ld16(taddr + cb, v);
-          if (ncols > 16) tc::tmem_ld16(taddr + cb + 16, v2);
+          ld_acc(cb, v);
+          if (ncols > 16) ld_acc(cb + 16, v2);
 #pragma unroll
           for (int i = 0; i < 16; ++i) tT[lane * 33 + i] = v[i];
           if (ncols > 16) {
@@ -717,7 +748,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const hdn_dgrad_epi& E = p.epi[0];
         const hdn_src& S = p.esrc[0];
         for (int cc = 0; cc < p.BN; cc += 16) {
-          tc::tmem_ld16(taddr + cc, v);
+          ld_acc(cc, v);
           if (!rvalid) continue;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
@@ -760,8 +791,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int cb = 0; cb < p.BN; cb += 32) {
           const int ncols = min(32, p.BN - cb);
           float v2[16];
-          tc::tmem_ld16(taddr + cb, v);
-          if (ncols > 16) tc::tmem_ld16(taddr + cb + 16, v2);
+          ld_acc(cb, v);
+          if (ncols > 16) ld_acc(cb + 16, v2);
 #pragma unroll
           for (int i = 0; i < 16; ++i) tT[lane * 33 + i] = rvalid ? v[i] : 0.f;
           if (ncols > 16) {
@@ -863,7 +894,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 //   role 1 (dgrad): B[n][k] = w[flip(tap)][n][k]                 K = Cout, NC = Cin
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int Cin, int Cout, int kd, int kh, int kw, int BN, int KB,
-                                                           int KC, int role, int nsplit, long long total16) {
+                                                           int KC, int role, int nsplit, int fold, long long total16) {
   // one thread per 16-byte output unit (n, chunk j): 8 consecutive k.  role 0 reads w[tap][k][col] (threads
   // adjacent in n -> coalesced over col); role 1 reads w[tap'][col][k..k+8) (two float4 per thread).
   const int T = kd * kh * kw;
@@ -872,8 +903,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     long long t = idx;
     const int n = (int)(t % BN); t /= BN;
     const int nj = KC / 8;
-    const int j = (int)(t % nj); t /= nj;
-    const int part = (int)(t % nsplit); t /= nsplit;
+    int j, part;                         // fold: [chunk j][part][n] (head and tail rows side by side along N), else [part][chunk j][n]
+    if (fold) { part = (int)(t % nsplit); t /= nsplit; j = (int)(t % nj); t /= nj; }
+    else      { j = (int)(t % nj); t /= nj; part = (int)(t % nsplit); t /= nsplit; }
     const int tap = (int)(t % T); t /= T;
     const int kb = (int)(t % KB); t /= KB;
     const int nt = (int)t;
@@ -908,7 +940,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 //   role 1 (dgrad): B[n = (rd,rh,rw,c)][k = co] = w[t(3 - tq', r)][c][co]   (taps flipped)
 __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                                int Cin, int Cout, int three_d, int BN, int KB, int KC,
-                                                               int role, int nsplit, long long total16) {
+                                                               int role, int nsplit, int fold, long long total16) {
   const int TD = three_d ? 4 : 1, T = TD * 16;
   const int quads = three_d ? 8 : 4;
   const int K = role == 0 ? quads * 4 : Cout, NC = role == 0 ? Cout : quads * 4;
@@ -917,8 +949,9 @@ __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __re
     long long t = idx;
     const int n = (int)(t % BN); t /= BN;
     const int nj = KC / 8;
-    const int j = (int)(t % nj); t /= nj;
-    const int part = (int)(t % nsplit); t /= nsplit;
+    int j, part;
+    if (fold) { part = (int)(t % nsplit); t /= nsplit; j = (int)(t % nj); t /= nj; }
+    else      { j = (int)(t % nj); t /= nj; part = (int)(t % nsplit); t /= nsplit; }
     int tap = (int)(t % T); t /= T;
     const int kb = (int)(t % KB); t /= KB;
     const int nt = (int)t;
@@ -968,6 +1001,16 @@ int hdn_tc_fastx() {
   return v;
 }
 
+// HDN_TC_X3FOLD=1 (and a library built with -DHDN_TC_X3FOLD): experiment switch, see TcParams::fold (default 0)
+int hdn_tc_x3fold() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HDN_TC_X3FOLD");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v;
+}
+
 // HDN_TC_L2PF=1: experiment switch, see TcParams::l2pf (default 0)
 int hdn_tc_l2pf() {
   static int v = -1;
@@ -981,6 +1024,7 @@ int hdn_tc_l2pf() {
 namespace {
 
 struct TcPlan {
+  int fold;
   int BN, n_tiles, KB, CK, nsb, nraw, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
   int PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], raw_bytes, tab_src[2], tab_vq[2], tab_ints;
   long long ws_elems;
@@ -1082,8 +1126,9 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   pl.raw_bytes = (off + 127) / 128 * 128;
   pl.tab_ints = toff;
   const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * pl.CK * 2 * nsplit;
+  pl.fold = (kFold && nsplit == 2 && hdn_tc_x3fold() && pl.BN <= 128) ? 1 : 0;
   int cols = 32;
-  while (cols < 2 * pl.BN) cols *= 2;                      // two accumulator buffers
+  while (cols < 2 * pl.BN * (pl.fold ? 2 : 1)) cols *= 2;  // two accumulator buffers
   pl.tmem_cols = cols;
   pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * pl.CK * nsplit;
   const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES +
@@ -1131,9 +1176,9 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     long long total = pl.ws_elems / 8;
     unsigned gr = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     if (g.s2d || g.scatter)
-      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, total);
+      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, total);
     else
-      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, total);
+      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, total);
     HDN_CHECK_LAUNCH("pack_weights");
   }
   TcParams p;
@@ -1157,6 +1202,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.split = nsplit == 2 ? 1 : 0;
   p.fastx = hdn_tc_fastx();
   p.l2pf = hdn_tc_l2pf();
+  p.fold = pl.fold;
   if (mode == 0) {
     p.nsrc = c->nsrc;
     p.src[0] = c->src[0];

@@ -21,6 +21,7 @@
  *       HDN_TC_FASTX=0|1|2  operand-transform form of the tcgen05 kernels (default 2)
  *       HDN_POOL_FAST=0|1   vector max-pool backward (default 1)
  *       HDN_TC_L2PF=0|1     L2::256B prefetch hint on the raw patch copies (default 0, experiment)
+ *       HDN_TC_X3FOLD=0|1   folded bf16x3 issue scheme (default 0, experiment; needs a -DHDN_TC_X3FOLD build)
  */
 #ifndef HDN_H_
 #define HDN_H_

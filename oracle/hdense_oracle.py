@@ -3,7 +3,7 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this file.  Nothing under the product package imports it.
 
-PARITY UNPINNED for conv / batch-norm / pooling / softmax / SGD / losses / whole
+PARITY UNPINNED for conv / batch-norm / pooling / SGD / losses / whole
 models: the reference's arithmetic lives in TensorFlow 1.x (requirements.txt:71-72,
 `tensorflow==1.5.1`), which is neither vendored under /root/reference nor importable
 here, and the reference ships no golden vectors for this path.
@@ -11,6 +11,8 @@ What IS pinned (tests/test_oracle.py):
   * upsampling == np.repeat      (Keras-2.0.8/tests/keras/layers/convolutional_test.py:673-681,726-736)
   * zero padding                 (same file :508-628)
   * add / concatenate            (Keras-2.0.8/tests/keras/layers/merge_test.py:13-30,142-177)
+  * softmax, relu                (Keras-2.0.8/tests/keras/activations_test.py:53-68,158-164: the upstream test's own
+                                  NumPy reference on its standard values)
   * every op against an independent direct-loop NumPy fp64 restatement of the TF op
     semantics (oracle/naive_ops.py) on tiny shapes.
 
@@ -142,10 +144,10 @@ def conv_block(ctx, x, stage, branch, learn, pre=""):
     """hybridnet.py:264-298 / densenet.py:103-137 (2D), hybridnet.py:11-45 (3D, pre='3d')."""
     base = "%sconv%d_%d" % (pre, stage, branch)
     y = bn(ctx, x, base + "_x1_bn", EPS_DENSE, learn)
-    y = F.relu(scale(ctx, y, base + "_x1_scale"))
+    y = relu(scale(ctx, y, base + "_x1_scale"))
     y = conv(ctx, y, base + "_x1", use_bias=False)
     y = bn(ctx, y, base + "_x2_bn", EPS_DENSE, learn)
-    y = F.relu(scale(ctx, y, base + "_x2_scale"))
+    y = relu(scale(ctx, y, base + "_x2_scale"))
     y = zero_pad(y, 1)
     return conv(ctx, y, base + "_x2", use_bias=False)
 
@@ -163,7 +165,7 @@ def transition_block(ctx, x, stage, learn, pre=""):
     """hybridnet.py:301-327 (2D: avgpool 2x2) / :71-97 (3D: avgpool (2,2,1))."""
     base = "%sconv%d_blk" % (pre, stage)
     y = bn(ctx, x, base + "_bn", EPS_DENSE, learn)
-    y = F.relu(scale(ctx, y, base + "_scale"))
+    y = relu(scale(ctx, y, base + "_scale"))
     y = conv(ctx, y, base, use_bias=False)
     return avg_pool(y, 2 if _nd(y) == 2 else (2, 2, 1))
 
@@ -178,7 +180,7 @@ def dense_unet_2d(ctx, x, learn_bn, skip=False, dropout_rate=0.0):
     y = zero_pad(x, 3)
     y = conv(ctx, y, "conv1", strides=2, use_bias=False)
     y = bn(ctx, y, "conv1_bn", EPS_DENSE, learn_bn)
-    y = F.relu(scale(ctx, y, "conv1_scale"))
+    y = relu(scale(ctx, y, "conv1_scale"))
     box.append(y)
     y = max_pool(zero_pad(y, 1), 3, 2)
     for bi in range(3):
@@ -188,7 +190,7 @@ def dense_unet_2d(ctx, x, learn_bn, skip=False, dropout_rate=0.0):
         y = transition_block(ctx, y, stage, learn_bn)
     y = dense_block(ctx, y, 5, nb_layers[3], learn_bn)
     y = bn(ctx, y, "conv5_blk_bn", EPS_DENSE, learn_bn)
-    y = F.relu(scale(ctx, y, "conv5_blk_scale"))
+    y = relu(scale(ctx, y, "conv5_blk_scale"))
     box.append(y)
     for k in range(5):
         y = upsample(y, (2, 2))
@@ -200,7 +202,7 @@ def dense_unet_2d(ctx, x, learn_bn, skip=False, dropout_rate=0.0):
         y = conv(ctx, y, "conv_up%d" % k, padding="same")
         if k == 4 and dropout_rate:
             y = dropout(ctx, y, "conv_up4_dropout", dropout_rate)      # densenet.py:92
-        y = F.relu(bn(ctx, y, "bn_up%d" % k, EPS_KERAS, learn_bn))
+        y = relu(bn(ctx, y, "bn_up%d" % k, EPS_KERAS, learn_bn))
     feat = y
     logits = conv(ctx, feat, "dense167classifer", padding="same")
     return feat, logits
@@ -215,7 +217,7 @@ def dense_net_3d(ctx, x, learn_dense, learn_other=True):
     y = zero_pad(x, 3)
     y = conv(ctx, y, "3dconv1", strides=2, use_bias=False)
     y = bn(ctx, y, "3dconv1_bn", EPS_DENSE, learn_other)
-    y = F.relu(scale(ctx, y, "3dconv1_scale"))
+    y = relu(scale(ctx, y, "3dconv1_scale"))
     y = max_pool(zero_pad(y, 1), 3, 2)
     for bi in range(3):
         stage = bi + 2
@@ -223,12 +225,12 @@ def dense_net_3d(ctx, x, learn_dense, learn_other=True):
         y = transition_block(ctx, y, stage, learn_dense, pre="3d")
     y = dense_block(ctx, y, 5, nb_layers[3], learn_dense, pre="3d")
     y = bn(ctx, y, "3dconv5_blk_bn", EPS_DENSE, learn_other)
-    y = F.relu(scale(ctx, y, "3dconv5_blk_scale"))
+    y = relu(scale(ctx, y, "3dconv5_blk_scale"))
     ups = [(2, 2, 1), (2, 2, 1), (2, 2, 1), (2, 2, 2), (2, 2, 2)]
     for k in range(5):
         y = upsample(y, ups[k])
         y = conv(ctx, y, "3dconv_up%d" % k, padding="same")
-        y = F.relu(bn(ctx, y, "3dbn_up%d" % k, EPS_KERAS, learn_other))
+        y = relu(bn(ctx, y, "3dbn_up%d" % k, EPS_KERAS, learn_other))
     return y
 
 
@@ -261,12 +263,23 @@ def hybrid_net(ctx, vol, variant="end2end", dropout_rate=None):
     y = conv(ctx, y, "fianl_conv", padding="same")
     rate = dropout_rate if dropout_rate is not None else (0.3 if variant == "end2end" else 0.1)
     y = dropout(ctx, y, "fianl_conv_dropout", rate)
-    y = F.relu(bn(ctx, y, "final_bn", EPS_KERAS, True))
+    y = relu(bn(ctx, y, "final_bn", EPS_KERAS, True))
     y = conv(ctx, y, "2d3dclassifer", padding="same")
     return y.permute(0, 2, 3, 4, 1)                                  # (B,H,W,S,3)
 
 
 # -------------------------------------------------------------------------- losses
+def softmax(x, axis=-1):
+    """K.softmax (KB:2708 -> tf.nn.softmax over the last axis).  Pinned by the upstream known-answer test
+    Keras-2.0.8/tests/keras/activations_test.py:53-68 (tests/test_oracle.py)."""
+    return torch.softmax(torch.as_tensor(x), dim=axis)
+
+
+def relu(x):
+    """K.relu (KB:2671, alpha = 0, no max_value).  Pinned by activations_test.py:158-164."""
+    return F.relu(torch.as_tensor(x))
+
+
 def weighted_crossentropy(y_true, y_pred, crop=True):
     """loss.py:5-25 (crop=True: hybrid, drops first/last slice; `1:7` generalised to `1:S-1`,
     identical for the reference's S=8) and loss.py:27-46 (crop=False: 2D).
@@ -278,7 +291,7 @@ def weighted_crossentropy(y_true, y_pred, crop=True):
         y_true = y_true[:, :, :, 1:S - 1]
     lp = y_pred.reshape(-1, 3)
     yt = torch.as_tensor(y_true, dtype=lp.dtype).reshape(-1)
-    sm = torch.softmax(lp, dim=1)
+    sm = softmax(lp, axis=1)
     lg = torch.log(torch.clamp(sm, 1e-10, 1.0))
     w = torch.tensor(CLASS_W, dtype=lp.dtype)
     tot = lp.new_zeros(())
@@ -359,7 +372,7 @@ def predict_tumor_inwindow(predict_fn, imgs, num, mini, maxi, size, cols):
     for c in window_starts(z, mini[2], maxi[2], cols):
         box[0, :, :, :, 0] = imgs[0:size, 0:size, c:c + cols]
         lg = torch.as_tensor(predict_fn(box))
-        pm = torch.softmax(lg, dim=-1).numpy()[:, :, :, 1:-1, :]
+        pm = softmax(lg, axis=-1).numpy()[:, :, :, 1:-1, :]
         score[0:size, 0:size, c + 1:c + cols - 1, :] += pm[0]
         cnt[0:size, 0:size, c + 1:c + cols - 1, :] += 1
     score = score / (cnt + 1e-4)

@@ -1,7 +1,8 @@
 """Pins the CPU oracle (oracle/hdense_oracle.py):
   * against the numerically pinned upstream Keras tests that exist for this path -- UpSampling2D/3D == np.repeat
     (Keras-2.0.8/tests/keras/layers/convolutional_test.py:673-681,726-736), ZeroPadding2D/3D: zero border, interior
-    untouched (same file :508-628), Add / Concatenate (Keras-2.0.8/tests/keras/layers/merge_test.py:13-30,142-177);
+    untouched (same file :508-628), Add / Concatenate (Keras-2.0.8/tests/keras/layers/merge_test.py:13-30,142-177),
+    softmax against the NumPy reference inside Keras-2.0.8/tests/keras/activations_test.py:53-68 and relu (:158-164);
   * against oracle/naive_ops.py, an independent direct-loop NumPy fp64 restatement of each TF op, on tiny shapes;
   * against the committed fixtures in tests/golden/ (made by tests/golden/make_golden.py from the oracle itself: they
     guard against drift, they are NOT reference outputs -- TensorFlow 1.x is not installable here, so conv / BN /
@@ -60,6 +61,26 @@ def test_add_and_concat():
 
 def _ctx(params, training=True):
     return orc.Ctx(params, training, dtype=torch.float64)
+
+
+def test_softmax_and_relu_known_answers():
+    """Keras-2.0.8/tests/keras/activations_test.py: softmax against the test's own NumPy reference on its standard
+    values (:53-68, rtol 1e-5), relu is the identity on them (:158-164); plus the sign case the upstream test omits."""
+    vals = np.array([[0, 0.1, 0.5, 0.9, 1.0]], dtype=np.float32)          # get_standard_values(), :11-14
+
+    def softmax_ref(values):                                               # :56-59
+        m = np.max(values)
+        e = np.exp(values - m)
+        return e / np.sum(e)
+
+    np.testing.assert_allclose(orc.softmax(vals).numpy(), softmax_ref(vals), rtol=1e-5)
+    np.testing.assert_allclose(orc.relu(vals).numpy(), vals, rtol=1e-5)
+    assert np.array_equal(orc.relu(np.array([-1.5, -0.0, 2.0], np.float32)).numpy(), np.array([0.0, 0.0, 2.0], np.float32))
+    # the loss takes the soft-max over the class axis of every voxel (loss.py:9): rows are independent
+    x = np.random.default_rng(0).normal(0, 3, (7, 3)).astype(np.float32)
+    got = orc.softmax(x, axis=1).numpy()
+    for i in range(7):
+        np.testing.assert_allclose(got[i], softmax_ref(x[i]), rtol=1e-5)
 
 
 def test_conv_against_direct_loops():

@@ -98,7 +98,8 @@ def _worker(rank, world, port, out):
     m, a, vol, mini, maxi = _model_and_volume()
     mine = shard_windows(window_starts(20, 4, 15, 8), world, rank)
     s1, s2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a)
-    res = {"n_windows": len(mine), "s1": s1, "s2": s2}
+    r1, r2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a, reuse_2d=True)     # sharding + 2-D slice reuse together
+    res = {"n_windows": len(mine), "s1": s1, "s2": s2, "reuse_equal": bool(np.array_equal(s1, r1) and np.array_equal(s2, r2))}
     if rank == 0:
         o1, o2 = _oracle_result(m, vol, mini, maxi)
         res["e1"], res["e2"] = float(np.abs(s1 - o1).max()), float(np.abs(s2 - o2).max())
@@ -120,6 +121,7 @@ def test_predict_tumor_inwindow_two_ranks_gloo():
     assert out[0]["n_windows"] > 0 and out[1]["n_windows"] > 0
     assert out[0]["e1"] < 1e-4 and out[0]["e2"] < 1e-4                      # sharded result == the reference loop
     assert np.array_equal(out[0]["s1"], out[1]["s1"]) and np.array_equal(out[0]["s2"], out[1]["s2"])
+    assert out[0]["reuse_equal"] and out[1]["reuse_equal"]
 
 
 def test_new_slices_of_a_moved_window():

@@ -177,12 +177,15 @@ def profile_step(model, net, steps):
         model.train_step_device(net)
     torch.cuda.synchronize()
     agg, ops = {}, {}
-    for key, flops, s, e, name in be.prof:
+    for ent in be.prof:
+        key, flops, s, e, name = ent[:5]
+        nbytes = ent[5] if len(ent) > 5 else 0.0
         t = s.elapsed_time(e)
-        a = agg.setdefault(key, [0.0, 0.0, 0])
+        a = agg.setdefault(key, [0.0, 0.0, 0, 0.0])
         a[0] += t
         a[1] += flops
         a[2] += 1
+        a[3] += nbytes
         if flops:
             o = ops.setdefault((key, name), [0.0, 0.0, 0])
             o[0] += t
@@ -306,8 +309,13 @@ def run_gpu(a):
                             "flop_per_launch": fl,
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if "[tc" in k and sustained
                             else ("fallback 1.4 PF" if "[tc" in k else "fp32 FMA nominal at max SM clock")}
+        hbm_peak = peaks.get("hbm_gbs") or 6400.0           # measured copy bandwidth (MEASURED_PEAKS.json), else nominal fallback
+        # per class: tensor rate of the algorithmic flops AND HBM rate of the algorithmic bytes (fp32 activations moved
+        # once) -- the 1x1 layers of the dense blocks are bounded by the second
         line["kernel_classes"] = {kk: {"ms": round(v[0] / a.profile_steps, 3), "tflops": round(v[1] / max(v[0], 1e-9) / 1e9, 2),
-                                        "launches": v[2] // a.profile_steps}
+                                        "launches": v[2] // a.profile_steps,
+                                        "hbm_gbs": round(v[3] / max(v[0], 1e-9) / 1e6, 1),
+                                        "hbm_frac": round(v[3] / max(v[0], 1e-9) / 1e6 / hbm_peak, 4)}
                                   for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
         line["launch_gaps"] = gaps
         # CPU baseline on this box's host cores, bounded sample

@@ -133,8 +133,9 @@ class CudaBackend(object):
         self.prof = None          # list of (key, flops, start_event, end_event, op name) while profiling
         self._cur = ""
 
-    def _run(self, key, flops, n_launch, fn, *args):
-        """Issue one C-ABI call; with profiling on, bracket it with CUDA events on the launch stream."""
+    def _run(self, key, flops, n_launch, fn, *args, nbytes=0.0):
+        """Issue one C-ABI call; with profiling on, bracket it with CUDA events on the launch stream.
+        prof entries: (class key, algorithmic flops, start event, end event, op name, algorithmic HBM bytes)."""
         self.launches += n_launch
         if self.prof is None:
             return fn(*args)
@@ -142,7 +143,7 @@ class CudaBackend(object):
         s.record()
         rc = fn(*args)
         e.record()
-        self.prof.append((key, flops, s, e, self._cur))
+        self.prof.append((key, flops, s, e, self._cur, nbytes))
         return rc
 
     @staticmethod
@@ -152,6 +153,21 @@ class CudaBackend(object):
     @staticmethod
     def _conv_flops(d):
         return 2.0 * d.out.M * d.Cin * d.Cout * d.k[0] * d.k[1] * d.k[2]
+
+    def _conv_bytes(self, d, which, epis=None):
+        """Algorithmic HBM bytes of one convolution pass (fp32 activations read / written once; weights and the
+        halo re-reads of neighbouring tiles not counted): the numerator of the HBM roofline of the 1x1 layers."""
+        if self.prof is None:
+            return 0.0
+        m_out = float(d.out.M) * d.Cout
+        src = [float(s.act.view.M) * d.Cin for s in d.srcs]
+        if which == 1:
+            b = m_out                                           # dY
+            for n, e in zip(src, epis):
+                if e.mode != 2:
+                    b += n * (3.0 if e.accumulate else 2.0)     # stored value (ReLU mask, S2) + gradient write (+ read)
+            return 4.0 * b
+        return 4.0 * (sum(src) + m_out)                         # fprop: sources + y;  wgrad: sources + dY
 
     @property
     def stream(self):
@@ -223,7 +239,7 @@ class CudaBackend(object):
     def conv_fprop(self, d):
         self._cur = d.name
         _lib.check(self._run(self._conv_key(d, "fprop"), self._conv_flops(d), 1, self.lib.hdn_conv_fprop,
-                             C.byref(self._conv(d)), self.stream), "hdn_conv_fprop " + d.name)
+                             C.byref(self._conv(d)), self.stream, nbytes=self._conv_bytes(d, 0)), "hdn_conv_fprop " + d.name)
 
     def conv_dgrad(self, d, epis):
         arr = d.__dict__.get("_c_epis")
@@ -235,13 +251,14 @@ class CudaBackend(object):
         nact = sum(1 for e in epis if e.mode != 2)
         self._cur = d.name
         _lib.check(self._run(self._conv_key(d, "dgrad"), self._conv_flops(d) * nact, nact, self.lib.hdn_conv_dgrad,
-                             C.byref(self._conv(d, True)), arr, self.stream), "hdn_conv_dgrad " + d.name)
+                             C.byref(self._conv(d, True)), arr, self.stream, nbytes=self._conv_bytes(d, 1, epis)),
+                   "hdn_conv_dgrad " + d.name)
 
     def conv_wgrad(self, d, dw, dbias):
         self._cur = d.name
         _lib.check(self._run(self._conv_key(d, "wgrad"), self._conv_flops(d), 1 + (dbias is not None),
                              self.lib.hdn_conv_wgrad, C.byref(self._conv(d, True)), dw.data_ptr(), _ptr(dbias),
-                             self.stream), "hdn_conv_wgrad " + d.name)
+                             self.stream, nbytes=self._conv_bytes(d, 2)), "hdn_conv_wgrad " + d.name)
 
     def _pool(self, d, y_grad):
         key = "_c_g" if y_grad else "_c_f"

@@ -26,7 +26,7 @@ int hdn_conv_dgrad_tc(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_t 
 int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st);
 
 extern "C" const char* hdn_last_error(void) { return g_err; }
-extern "C" int hdn_version(void) { return 100; }
+extern "C" int hdn_version(void) { return 110; }   // 110: precision 2 (bf16x3), hdn_conv_tc_plan
 
 extern "C" int hdn_conv_tc_supported(const hdn_conv* c, int pass) {
   if (!c || hdn_validate_conv(c) != HDN_OK) return 0;

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhdn.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc2_wgrad.cu", "elementwise.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -92,7 +92,7 @@ EXPORTS = [
     "hdn_bn_bwd_apply", "hdn_dropout_bwd", "hdn_col_stats", "hdn_wce_accum", "hdn_wce_grad",
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
     "hdn_window_accumulate", "hdn_window_finalize", "hdn_dev_malloc", "hdn_dev_free",
-    "hdn_ipc_get_handle", "hdn_ipc_open", "hdn_ipc_close",
+    "hdn_ipc_get_handle", "hdn_ipc_open", "hdn_ipc_close", "hdn_set_switch",
 ]
 
 _lib = None
@@ -140,6 +140,7 @@ def load():
         "hdn_ipc_get_handle": [vp, vp],
         "hdn_ipc_open": [vp, C.POINTER(vp)],
         "hdn_ipc_close": [vp],
+        "hdn_set_switch": [C.c_char_p, i32],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -24,9 +24,18 @@ long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass);
 int hdn_conv_fprop_tc(const hdn_conv* c, cudaStream_t st);
 int hdn_conv_dgrad_tc(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_t st);
 int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st);
+// second-generation weight gradient: bf16 operand pre-pass + TMA tile loads + tcgen05 (conv_tc2_wgrad.cu)
+int hdn_wgrad_tc2_enabled();
+void hdn_wgrad_tc2_set(int v);
+void hdn_tc2_layout_set(int v);
+int hdn_wgrad_tc2_supported(const hdn_conv* c);
+long long hdn_wgrad_tc2_workspace(const hdn_conv* c);
+int hdn_wgrad_tc2_plan_info(const hdn_conv* c, int* out);
+int hdn_conv_wgrad_tc2(const hdn_conv* c, float* dw, cudaStream_t st);
+static bool use_wgrad_tc2(const hdn_conv* c) { return hdn_wgrad_tc2_enabled() && hdn_wgrad_tc2_supported(c); }
 
 extern "C" const char* hdn_last_error(void) { return g_err; }
-extern "C" int hdn_version(void) { return 110; }   // 110: precision 2 (bf16x3), hdn_conv_tc_plan
+extern "C" int hdn_version(void) { return 200; }   // 200: tc2 weight gradient (TMA tile loads), hdn_set_switch, post-processing, layout kernels
 
 extern "C" int hdn_conv_tc_supported(const hdn_conv* c, int pass) {
   if (!c || hdn_validate_conv(c) != HDN_OK) return 0;
@@ -35,7 +44,17 @@ extern "C" int hdn_conv_tc_supported(const hdn_conv* c, int pass) {
 
 extern "C" int64_t hdn_conv_tc_workspace(const hdn_conv* c, int pass) {
   if (!c || hdn_validate_conv(c) != HDN_OK) return 0;
+  if (pass == 2 && hdn_tc_supported(c, 2) && use_wgrad_tc2(c)) return (int64_t)hdn_wgrad_tc2_workspace(c);
   return (int64_t)hdn_tc_workspace_bytes(c, pass);
+}
+
+// Process-wide switches (the environment variables of the same name set the defaults, see the top of hdn.h).
+extern "C" int hdn_set_switch(const char* name, int value) {
+  HDN_CHECK_ARG(name != nullptr, "set_switch: null name");
+  if (!strcmp(name, "HDN_WGRAD_TC2")) { hdn_wgrad_tc2_set(value); return HDN_OK; }
+  if (!strcmp(name, "HDN_TC2_LAYOUT")) { hdn_tc2_layout_set(value); return HDN_OK; }
+  hdn_set_error("set_switch: unknown switch %s", name);
+  return HDN_ERR_ARG;
 }
 
 int hdn_tc_plan_info(const hdn_conv* c, int pass, int* out);
@@ -45,6 +64,7 @@ extern "C" int hdn_conv_tc_plan(const hdn_conv* c, int pass, int32_t* out16) {
   if (rc) return rc;
   HDN_CHECK_ARG(out16 != nullptr && pass >= 0 && pass <= 2, "conv_tc_plan: bad arguments");
   if (!hdn_tc_supported(c, pass)) { hdn_set_error("conv_tc_plan: tcgen05 path does not take this shape"); return HDN_ERR_UNSUPPORTED; }
+  if (pass == 2 && use_wgrad_tc2(c)) return hdn_wgrad_tc2_plan_info(c, out16);
   return pass == 2 ? hdn_wgrad_plan_info(c, out16) : hdn_tc_plan_info(c, pass, out16);
 }
 
@@ -86,6 +106,7 @@ extern "C" int hdn_conv_wgrad(const hdn_conv* c, float* dw, float* dbias, void* 
   }
   if (c->precision == 1 || c->precision == 2) {
     if (!hdn_tc_supported(c, 2)) { hdn_set_error("conv_wgrad: tcgen05 path does not take this shape"); return HDN_ERR_UNSUPPORTED; }
+    if (use_wgrad_tc2(c)) return hdn_conv_wgrad_tc2(c, dw, (cudaStream_t)stream);
     return hdn_conv_wgrad_tc(c, dw, (cudaStream_t)stream);
   }
   return hdn_conv_wgrad_simt(c, dw, (cudaStream_t)stream);

@@ -22,6 +22,10 @@
  *       HDN_POOL_FAST=0|1   vector max-pool backward (default 1)
  *       HDN_TC_L2PF=0|1     L2::256B prefetch hint on the raw patch copies (default 0, experiment)
  *       HDN_TC_X3FOLD=0|1   folded bf16x3 issue scheme (default 0, experiment; needs a -DHDN_TC_X3FOLD build)
+ *       HDN_WGRAD_TC2=0|1   weight gradients of the 1x3x3 / 3x3x3 convolutions (precision 1) through the bf16 pre-pass +
+ *                           TMA tile-load kernel (default 1; 0 = first-generation kernel); also hdn_set_switch()
+ *       HDN_TC2_LAYOUT=0|1  shared-memory operand layout of that kernel: 0 = 16-byte chunk planes (SWIZZLE_NONE),
+ *                           1 = 128-byte swizzled 64-channel rows
  */
 #ifndef HDN_H_
 #define HDN_H_
@@ -39,6 +43,8 @@ typedef enum {
 
 const char* hdn_last_error(void);
 int hdn_version(void);
+/* Set a process-wide switch by its environment-variable name (tests flip kernels inside one process). */
+int hdn_set_switch(const char* name, int value);
 
 typedef struct {
   const float* p;   /* base pointer (device) */

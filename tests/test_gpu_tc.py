@@ -219,3 +219,45 @@ def test_wgrad_tc_vs_fp32(cuda_dev, name, prec):
     assert rel_l2(w1, w0) < TOL, (name, rel_l2(w1, w0))
     if b0 is not None:
         assert rel_l2(b1, b0) < 1e-4
+
+
+# ---- second-generation weight gradient (conv_tc2_wgrad.cu: bf16 pre-pass + TMA tile loads + tcgen05) ---------------
+W2 = ["3x3_dense", "3x3x3_dense", "3x3_up_skip_bias_stats", "3x3x3_up222_bias_stats", "3x3x3_up122_504", "3x3_wide",
+      "3x3x3_two_src"]
+W2_EXTRA = {
+    # ragged grid (H, W not multiples of the 16 x 8 tile), channel tails inside a 128-channel tile / a 64-channel block
+    "3x3x3_ragged": dict(N=2, D=3, H=20, W=12, cin=96, cout=64, k=(3, 3, 3), bias=True),
+    "3x3_ragged_c200": dict(N=1, D=2, H=24, W=20, cin=200, cout=72, k=(1, 3, 3)),
+}
+
+
+def _switch(name, value):
+    from h_denseunet_b200 import _lib
+    _lib.check(_lib.load().hdn_set_switch(name.encode(), int(value)), "hdn_set_switch")
+
+
+@pytest.mark.parametrize("layout", [0, 1], ids=["planes", "sw128"])
+@pytest.mark.parametrize("name", W2 + sorted(W2_EXTRA))
+def test_wgrad_tc2_vs_fp32_and_gen1(cuda_dev, name, layout):
+    """tc2 weight gradient against the fp32 FMA kernel (bf16 operand bound) and against the first-generation tcgen05
+    kernel: identical bf16 operands, fp32 accumulation in another order -> 1e-4."""
+    kw = dict(CASES.get(name) or W2_EXTRA[name])
+    kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
+    _switch("HDN_WGRAD_TC2", 1)
+    _switch("HDN_TC2_LAYOUT", layout)
+    try:
+        c = Case(cuda_dev, tc=1, **kw)
+        assert c.supported[2] == 1
+        c.op.desc.precision = 1
+        assert c.net.be.conv_tc_workspace(c.op.desc, 2) > 0, "tc2 does not take %s" % name   # gen 1 needs no wgrad scratch
+        w0, b0 = _wgrad(c, 0)
+        w2, b2 = _wgrad(c, 1)
+        _switch("HDN_WGRAD_TC2", 0)
+        w1, _ = _wgrad(c, 1)
+    finally:
+        _switch("HDN_WGRAD_TC2", 1)
+        _switch("HDN_TC2_LAYOUT", 0)
+    assert rel_l2(w2, w0) < TOLS[1], (name, rel_l2(w2, w0))
+    assert rel_l2(w2, w1) < 1e-4, (name, rel_l2(w2, w1))
+    if b0 is not None:
+        assert rel_l2(b2, b0) < 1e-4

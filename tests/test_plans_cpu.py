@@ -51,7 +51,13 @@ def test_every_convolution_has_a_valid_plan(plan_rows, prec):
             assert bne == bn * (2 if prec == 2 else 1) and bne <= 256, what
             assert ci == (64 if prec == 2 else 128), what
             assert ring * bne <= tmem, what                        # one accumulator per tap of the group
-            assert ws == 0, what
+            if ws:
+                # second-generation kernel (conv_tc2_wgrad.cu): plain bf16 only, 1x3x3 / 3x3x3; scratch = the two bf16
+                # operand tensors of the pre-pass; `nraw` reports the depth of the TMA stage ring
+                assert prec == 1 and P in (180, 160, 128) and 2 <= nraw <= 6, what
+                assert ws % 256 == 0, what
+            else:
+                assert prec == 2 or P == 128 or s2d, what          # gen 1 keeps bf16x3, the 1x1x1 layers and the stems
 
 
 def test_bf16x3_workspace_is_twice_the_bf16_one_per_channel_block(plan_rows):

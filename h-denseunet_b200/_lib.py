@@ -92,7 +92,7 @@ EXPORTS = [
     "hdn_bn_bwd_apply", "hdn_dropout_bwd", "hdn_col_stats", "hdn_wce_accum", "hdn_wce_grad",
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
     "hdn_window_accumulate", "hdn_window_finalize", "hdn_dev_malloc", "hdn_dev_free",
-    "hdn_ipc_get_handle", "hdn_ipc_open", "hdn_ipc_close", "hdn_set_switch",
+    "hdn_ipc_get_handle", "hdn_ipc_open", "hdn_ipc_close", "hdn_set_switch", "hdn_dp_signal", "hdn_dp_wait", "hdn_layout_nhws_to_nshw",
 ]
 
 _lib = None
@@ -141,6 +141,9 @@ def load():
         "hdn_ipc_open": [vp, C.POINTER(vp)],
         "hdn_ipc_close": [vp],
         "hdn_set_switch": [C.c_char_p, i32],
+        "hdn_dp_signal": [vp, i32, i32, C.c_uint32, vp],
+        "hdn_dp_wait": [vp, i32, C.c_uint32, vp],
+        "hdn_layout_nhws_to_nshw": [vp, vp, i32, i32, i32, i32, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -466,6 +466,50 @@ __global__ void __launch_bounds__(ET) dp_reduce_sgd_kernel(const PeerTable t, fl
   }
 }
 
+// Device-side step flags of the data-parallel exchange (peer-mapped, one uint32 slot per (owner, writer) pair): the
+// gradient / parameter arenas are handed over between the per-GPU processes on the compute stream itself, without a
+// host barrier.  signal: after a system-scope fence (everything this GPU's earlier kernels wrote is visible to its
+// peers) store `value` into slot [rank] of every peer's flag row.  wait: spin until all `world` slots of the local row
+// have reached `value`.
+struct FlagTable { unsigned int* f[16]; };
+__global__ void dp_signal_kernel(const FlagTable t, int world, int rank, unsigned int value) {
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    volatile unsigned int* q = t.f[threadIdx.x] + rank;
+    *q = value;
+    __threadfence_system();
+  }
+}
+__global__ void dp_wait_kernel(const unsigned int* flags, int world, unsigned int value) {
+  if (threadIdx.x < world) {
+    const volatile unsigned int* q = flags + threadIdx.x;
+    while ((int)(*q - value) < 0) __nanosleep(200);     // wrap-safe "slot < value"
+    __threadfence_system();
+  }
+}
+
+// --------------------------------------------------------------------------- host layout -> device layout
+// Reference volumes arrive as (N,H,W,S) (channel 1 dropped); the engine's layout is (N,S,H,W).  One pass over the
+// staged tensor, reads along W coalesced per slice through a 32x33 shared tile over (W, S).  T = float or short
+// (int16 label maps are converted to the fp32 the loss kernels read, train_hybrid.py:127-132).
+template <typename T>
+__global__ void __launch_bounds__(256) nhws_to_nshw_kernel(const T* __restrict__ in, float* __restrict__ out, int H, int W, int S) {
+  __shared__ float tile[32][33];
+  const int64_t nh = blockIdx.z;                      // n * H + h
+  const int n = (int)(nh / H), h = (int)(nh % H);
+  const int w0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {                   // rows = w, fastest = s (contiguous in the source)
+    const int w = w0 + i, sidx = s0 + tx;
+    if (w < W && sidx < S) tile[i][tx] = (float)in[(nh * W + w) * S + sidx];
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {                   // rows = s, fastest = w (contiguous in the destination)
+    const int sidx = s0 + i, w = w0 + tx;
+    if (w < W && sidx < S) out[(((int64_t)n * S + sidx) * H + h) * W + w] = tile[tx][i];
+  }
+}
+
 // --------------------------------------------------------------------------- sliding window
 __global__ void __launch_bounds__(ET) window_acc_kernel(const float* __restrict__ logits, float* __restrict__ score,
                                                          int S, int64_t HW, int z0) {
@@ -636,5 +680,28 @@ extern "C" int hdn_window_finalize(float* score, const int* count, int Z, int64_
   HDN_CHECK_ARG(score && count && Z > 0 && HW > 0, "window_finalize: bad arguments");
   window_fin_kernel<<<grid_for((int64_t)Z * HW, 2), ET, 0, ST>>>(score, count, Z, HW);
   HDN_CHECK_LAUNCH("window_finalize");
+  return HDN_OK;
+}
+
+extern "C" int hdn_dp_signal(unsigned int* const* peer_flags, int world, int rank, unsigned int value, void* stream) {
+  HDN_CHECK_ARG(peer_flags && world >= 1 && world <= 16 && rank >= 0 && rank < world, "dp_signal: bad arguments");
+  FlagTable t;
+  for (int r = 0; r < world; ++r) t.f[r] = peer_flags[r];
+  dp_signal_kernel<<<1, 32, 0, ST>>>(t, world, rank, value);
+  HDN_CHECK_LAUNCH("dp_signal");
+  return HDN_OK;
+}
+extern "C" int hdn_dp_wait(const unsigned int* flags, int world, unsigned int value, void* stream) {
+  HDN_CHECK_ARG(flags && world >= 1 && world <= 16, "dp_wait: bad arguments");
+  dp_wait_kernel<<<1, 32, 0, ST>>>(flags, world, value);
+  HDN_CHECK_LAUNCH("dp_wait");
+  return HDN_OK;
+}
+extern "C" int hdn_layout_nhws_to_nshw(const void* in, float* out, int N, int H, int W, int S, int is_int16, void* stream) {
+  HDN_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && S > 0 && (int64_t)N * H < 65536, "layout: bad arguments");
+  dim3 grid((unsigned)((W + 31) / 32), (unsigned)((S + 31) / 32), (unsigned)(N * H));
+  if (is_int16) nhws_to_nshw_kernel<short><<<grid, 256, 0, ST>>>(reinterpret_cast<const short*>(in), out, H, W, S);
+  else nhws_to_nshw_kernel<float><<<grid, 256, 0, ST>>>(reinterpret_cast<const float*>(in), out, H, W, S);
+  HDN_CHECK_LAUNCH("layout_nhws_to_nshw");
   return HDN_OK;
 }

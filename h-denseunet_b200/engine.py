@@ -792,7 +792,8 @@ class Net(object):
         self._accum_req = []
         self.accum = None
         self.compiled = False
-        self.step = 0
+        self.step = 0                 # optimizer steps taken (Model restores it from a checkpoint)
+        self.seed_salt = 0            # per run / per replica (Model sets it): replicas must not draw identical masks
         self.inputs = {}
         self.outputs = {}
         self.loss = None
@@ -818,6 +819,11 @@ class Net(object):
         cin = v0.C
         vdims = [v0.D * srcs[0].up[0], v0.H * srcs[0].up[1], v0.W * srcs[0].up[2]]
         od = [(vdims[i] + 2 * p[i] - k[i]) // s[i] + 1 for i in range(3)]
+        for i, x in enumerate(srcs[1:], 1):       # the Add in front of a convolution: same channels, batch and (up-sampled) grid
+            v = x.act.view
+            if (v.C, v.N, v.D * x.up[0], v.H * x.up[1], v.W * x.up[2]) != (cin, v0.N, vdims[0], vdims[1], vdims[2]):
+                raise ValueError("conv %s: source %d is (N=%d, C=%d, grid %s) but source 0 is (N=%d, C=%d, grid %s)" % (
+                    name, i, v.N, v.C, (v.D * x.up[0], v.H * x.up[1], v.W * x.up[2]), v0.N, cin, tuple(vdims)))
         if out is None:
             out = self.buffer(name, v0.N, od[0], od[1], od[2], cout).view()
         assert (out.N, out.D, out.H, out.W, out.C) == (v0.N, od[0], od[1], od[2], cout), (name, out.N, out.D, out.H,
@@ -873,7 +879,7 @@ class Net(object):
         raise RuntimeError("accum_alloc before compile")
 
     def step_seed(self, name):
-        return (zlib.crc32(name.encode()) & 0xFFFFFF) * 1000003 + self.step + 1
+        return ((zlib.crc32(name.encode()) & 0xFFFFFF) * 1000003 + self.step + 1 + self.seed_salt) & 0xFFFFFFFFFFFF
 
     def compile(self):
         assert not self.compiled

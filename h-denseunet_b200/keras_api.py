@@ -65,8 +65,11 @@ class Model(object):
         self.loss_fn = None
         self.dp = None
         self.stop_training = False
+        self.global_step = 0          # optimizer steps over the life of the weights (saved with them; drives the dropout stream)
+        self.run_seed = int(os.environ.get("HDN_RUN_SEED", "0"))
         self._staging = {}
         self._staging_ev = {}
+        self._copy_stream = None
         # register every parameter (host values, Keras default initialisers) without touching a device
         self._build(engine.Net(self.params, "meta", True, "fp32", backend=object(), dropout=False))
 
@@ -100,6 +103,9 @@ class Model(object):
             self._build(net)
             if training:
                 net.set_loss(net.outputs["logits"], bool(getattr(self.loss_fn, "crop", self.kind != "unet2d")))
+                rank = self.dp.rank if self.dp is not None else 0
+                net.seed_salt = (self.run_seed * 0x9E3779B1 + (rank + 1) * 0x85EBCA77) & 0xFFFFFFFF
+                net.step = self.global_step
             net.compile()
             self.nets[training] = net
         return net
@@ -121,82 +127,139 @@ class Model(object):
         return (self.b, self.size, self.size, self.cols, 4 if self.kind == "net3d" else 1)
 
     def _upload(self, net, x):
-        x = np.asarray(x, dtype=np.float32)
-        if tuple(x.shape) != self.input_shape:
-            raise ValueError("expected input of shape %s, got %s" % (self.input_shape, tuple(x.shape)))
+        x = self._check_input(x)
         buf = list(net.inputs.values())[0]
         self._h2d(x, buf.data, three_d=self.kind != "unet2d")
         return x.nbytes
 
-    def _h2d(self, x, dst, three_d):
-        """host (reference layout) -> device NDHWC through a pinned staging buffer.  The staging buffers keep the
-        host array's dtype (float32 volumes, int16 label maps -- half the bytes over PCIe and no host-side cast);
-        the conversion to the fp32 device tensor happens on the device, inside the layout-changing copy."""
+    # ---- host -> device staging ------------------------------------------------------------------------------
+    # Two slots of (pinned host buffer, device staging buffer) per array shape.  _stage copies the host array into the
+    # pinned buffer and starts the H2D copy on a dedicated copy stream; _unstage makes the compute stream wait for that
+    # copy and converts the staged reference layout into the engine's NDHWC buffer (hdn_layout_nhws_to_nshw for the
+    # (N,H,W,S,1) volumes and label maps; the int16 -> fp32 conversion of label maps happens there, on the device).
+    # fit_generator stages batch k+1 while step k runs, so the upload leaves the critical path.
+    def _stage(self, x, dev, slot=0):
         tdt = torch.int16 if x.dtype == np.int16 else torch.float32
         if tdt == torch.float32 and x.dtype != np.float32:
             x = np.asarray(x, dtype=np.float32)
-        key = (x.shape, dst.device, tdt)
+        key = (x.shape, dev, tdt, slot)
         st = self._staging.get(key)
+        cuda = dev.type == "cuda"
         if st is None:
-            pin = dst.device.type == "cuda"
-            need_dev = three_d or tdt != torch.float32
-            st = (torch.empty(x.shape, dtype=tdt, pin_memory=pin),
-                  torch.empty(x.shape, dtype=tdt, device=dst.device) if need_dev else None)
+            st = (torch.empty(x.shape, dtype=tdt, pin_memory=cuda), torch.empty(x.shape, dtype=tdt, device=dev))
             self._staging[key] = st
         ev = self._staging_ev.get(key)
         if ev is not None:
             ev.synchronize()          # the previous async copy out of this pinned buffer must have finished
         st[0].copy_(torch.from_numpy(np.ascontiguousarray(x)))
-        if three_d:    # (N,H,W,S,C) -> (N,S,H,W,C)
-            st[1].copy_(st[0], non_blocking=True)
-            dst.copy_(st[1].permute(0, 3, 1, 2, 4))
-        elif dst.shape[-1] != x.shape[-1] and dst.dim() == 5 and x.ndim == 4:
-            # 2-D input (N,H,W,3) into the 4-channel padded buffer (N,1,H,W,4); channel 3 stays zero
-            dst[:, 0, :, :, :x.shape[-1]].copy_(st[0], non_blocking=True)
-        elif st[1] is not None:
-            st[1].copy_(st[0], non_blocking=True)
-            dst.view(x.shape).copy_(st[1])
+        if cuda:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(self._copy_stream):
+                st[1].copy_(st[0], non_blocking=True)
+                if ev is None:
+                    ev = self._staging_ev[key] = torch.cuda.Event()
+                ev.record(self._copy_stream)
         else:
-            dst.view(x.shape).copy_(st[0], non_blocking=True)
-        if dst.device.type == "cuda":
-            if ev is None:
-                ev = self._staging_ev[key] = torch.cuda.Event()
-            ev.record()
-        return x.nbytes
+            st[1].copy_(st[0])
+        return key, x.nbytes
 
-    def _labels(self, net, y):
+    def _unstage(self, key, dst, three_d):
+        shape, dev, tdt, _ = key
+        src = self._staging[key][1]
+        if dev.type == "cuda":
+            torch.cuda.current_stream().wait_event(self._staging_ev[key])
+        if three_d and shape[-1] == 1 and dev.type == "cuda" and self.backend is None:
+            from . import _lib
+            N, H, W, S = shape[:4]
+            _lib.check(_lib.load().hdn_layout_nhws_to_nshw(src.data_ptr(), dst.data_ptr(), N, H, W, S, 1 if tdt == torch.int16 else 0,
+                                                           torch.cuda.current_stream().cuda_stream), "hdn_layout_nhws_to_nshw")
+        elif three_d:                 # (N,H,W,S,C) -> (N,S,H,W,C)
+            dst.copy_(src.permute(0, 3, 1, 2, 4))
+        elif dst.shape[-1] != shape[-1] and dst.dim() == 5 and len(shape) == 4:
+            # 2-D input (N,H,W,3) into the 4-channel padded buffer (N,1,H,W,4); channel 3 stays zero
+            dst[:, 0, :, :, :shape[-1]].copy_(src)
+        else:
+            dst.view(shape).copy_(src)
+
+    def _h2d(self, x, dst, three_d):
+        """host (reference layout) -> device NDHWC through the staging slots (see _stage / _unstage)."""
+        key, nbytes = self._stage(np.asarray(x), dst.device)
+        self._unstage(key, dst, three_d)
+        return nbytes
+
+    def _label_array(self, y):
         y = np.asarray(y)
         if y.dtype != np.int16:       # the reference feeds int16 label maps (train_hybrid.py:127-132); anything else as float
             y = np.asarray(y, dtype=np.float32)
-        lab = net.loss.labels
         if self.kind == "unet2d":
-            y = y.reshape(self.b, self.size, self.size)
-            return self._h2d(y, lab, three_d=False)
-        y = y.reshape(self.b, self.size, self.size, self.cols, 1)
-        return self._h2d(y, lab.view(lab.shape + (1,)), three_d=True)
+            return y.reshape(self.b, self.size, self.size)
+        return y.reshape(self.b, self.size, self.size, self.cols, 1)
+
+    def _label_dst(self, net):
+        lab = net.loss.labels
+        return lab if self.kind == "unet2d" else lab.view(lab.shape + (1,))
+
+    def _labels(self, net, y):
+        return self._h2d(self._label_array(y), self._label_dst(net), three_d=self.kind != "unet2d")
+
+    def _check_input(self, x):
+        x = np.asarray(x, dtype=np.float32)
+        if tuple(x.shape) != self.input_shape:
+            raise ValueError("expected input of shape %s, got %s" % (self.input_shape, tuple(x.shape)))
+        return x
+
+    def _stage_batch(self, net, x, y, slot):
+        """Start the upload of one (x, y) batch into staging slot `slot`; returns the handle _launch_staged takes."""
+        if self.dp is not None and len(x) == self.b * self.dp.world:
+            x, y = x[self.dp.rank * self.b:(self.dp.rank + 1) * self.b], y[self.dp.rank * self.b:(self.dp.rank + 1) * self.b]
+        dev = net.device
+        kx, nx = self._stage(self._check_input(x), dev, slot)
+        ky, ny = self._stage(self._label_array(y), dev, slot)
+        return kx, ky, nx + ny
+
+    def _launch_staged(self, net, handle):
+        """Enqueue one optimizer step on a staged batch (no host synchronisation); the loss is read by the caller."""
+        kx, ky, nbytes = handle
+        three_d = self.kind != "unet2d"
+        self._unstage(kx, list(net.inputs.values())[0].data, three_d)
+        self._unstage(ky, self._label_dst(net), three_d)
+        self.h2d_bytes = nbytes
+        self._step_kernels(net)
 
     def train_on_batch(self, x, y, **kwargs):
         if self.optimizer is None:
             raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
         net = self._net(True)
+        if self.dp is not None and len(x) == self.b * self.dp.world:
+            # the reference feeds the merged batch and slices it into towers (multi_gpu.py:20-33); here the tower is this rank
+            x, y = x[self.dp.rank * self.b:(self.dp.rank + 1) * self.b], y[self.dp.rank * self.b:(self.dp.rank + 1) * self.b]
         self.h2d_bytes = self._upload(net, x) + self._labels(net, y)
         return self.train_step_device(net)
 
     def train_step_device(self, net=None):
         """One optimizer step on whatever is resident in the input / label buffers."""
         net = net or self._net(True)
+        self._step_kernels(net)
+        return net.loss.value()
+
+    def _step_kernels(self, net):
+        if self.dp is not None:
+            self.dp.begin_step()          # peers have delivered the last update and released this replica's gradients
         net.forward()
         net.backward()
+        self.global_step = net.step
         o = self.optimizer
         if self.dp is not None:
             self.dp.step(net, o.lr, o.momentum)
         else:
             ps = self.params
             net.be.sgd(ps.train, ps.grads, ps.moms, ps.n_train, o.lr, o.momentum, 1.0)
-        return net.loss.value()
 
     def predict(self, x, batch_size=None, verbose=0, **kwargs):
         net = self._net(False)
+        if self.dp is not None:
+            self.dp.begin_step()
         self._upload(net, x)
         net.forward()
         return self._logits_to_host(net)
@@ -215,12 +278,24 @@ class Model(object):
         for cb in callbacks:
             if hasattr(cb, "set_model"):
                 cb.set_model(self)
+        if self.optimizer is None:
+            raise RuntimeError("You must compile a model before training/testing. Use `model.compile(optimizer, loss)`.")
+        net = self._net(True)
+        total = (int(epochs) - int(initial_epoch)) * int(steps_per_epoch)
+        slot, done = 0, 0
+        staged = self._stage_batch(net, *next(generator)[:2], slot=slot) if total > 0 else None
         for epoch in range(initial_epoch, epochs):
             losses = []
             t0 = time.time()
             for _ in range(int(steps_per_epoch)):
-                x, y = next(generator)[:2]
-                losses.append(self.train_on_batch(x, y))
+                # step k is enqueued, then batch k+1 is fetched from the generator and staged (pinned copy + H2D on the copy
+                # stream) while the GPU works; only then is step k's loss read back (the one host synchronisation per step)
+                self._launch_staged(net, staged)
+                done += 1
+                if done < total:
+                    slot ^= 1
+                    staged = self._stage_batch(net, *next(generator)[:2], slot=slot)
+                losses.append(net.loss.value())
             logs = {"loss": float(np.mean(losses))}
             history["loss"].append(logs["loss"])
             if verbose:
@@ -236,6 +311,8 @@ class Model(object):
     def get_weights_dict(self):
         """{'<layer>/<weight>': array} in the reference's (Keras) layouts: kernels HWIO / (kh,kw,ks,I,O)."""
         out = {}
+        if self.dp is not None and self.params.realised:
+            self.dp.begin_step()          # every peer's shard of the last update has landed
         for p in self.params.order:
             v = self.params.get_value(p.name)
             out[p.name] = self._to_keras(p.name, v)
@@ -271,6 +348,8 @@ class Model(object):
                     raise ValueError("unknown weight %s" % k)
                 continue
             self.params.set_value(k, self._from_keras(k, v))
+        if self.dp is not None and self.dp.ready:
+            self.dp._sync_initial(self.params)      # replicas stay identical: rank 0's values win (a collective call)
 
     def save_weights(self, path, overwrite=True):
         np.savez(path if path.endswith(".npz") else path + ".npz", **self.get_weights_dict())
@@ -322,5 +401,10 @@ def make_parallel(model, gpu_count, mini_batch=None):
                                "python -m torch.distributed.run --nproc-per-node %d ..." % (gpu_count, gpu_count))
         if dist.get_world_size() != gpu_count:
             raise ValueError("gpu_count=%d but world size is %d" % (gpu_count, dist.get_world_size()))
+        if mini_batch is not None and int(mini_batch) != model.b:
+            # multi_gpu.py:20-33: every tower sees `mini_batch` samples (BN batch statistics over those, not over args.b)
+            if model.nets:
+                raise RuntimeError("make_parallel(mini_batch=%d) after the model was realised with batch %d" % (mini_batch, model.b))
+            model.b = int(mini_batch)
         model.dp = DataParallel()
     return model

@@ -210,6 +210,18 @@ int hdn_dp_reduce_sgd(float* const* peer_p, const float* const* peer_g, float* m
                       int world, int rank, int64_t lo, int64_t hi, float lr, float mu,
                       float gscale, void* stream);
 
+/* Step flags of the data-parallel exchange: every process owns a row of `world` uint32 slots inside its peer-mapped
+ * arena.  hdn_dp_signal stores `value` into slot [rank] of every peer's row after a system-scope fence (stream-ordered
+ * after this GPU's gradient / parameter writes); hdn_dp_wait blocks the stream until every slot of the local row has
+ * reached `value`.  They replace the host barriers around hdn_dp_reduce_sgd (the reference has no counterpart: its
+ * towers live in one TF session, multi_gpu.py:35-53). */
+int hdn_dp_signal(unsigned int* const* peer_flags, int world, int rank, unsigned int value, void* stream);
+int hdn_dp_wait(const unsigned int* flags, int world, unsigned int value, void* stream);
+
+/* Host layout -> engine layout of a staged volume: in (N,H,W,S) float32 or int16 (the reference's
+ * (b, size, size, cols, 1) arrays, train_hybrid.py:66-133) -> out (N,S,H,W) float32. */
+int hdn_layout_nhws_to_nshw(const void* in, float* out, int N, int H, int W, int S, int is_int16, void* stream);
+
 /* Sliding-window accumulation (lib/funcs.py:28-47): softmax over 3 logits of a window
  * (1,S,H,W,3), slices 1..S-2 added into score (Z,H,W,2) [classes 1,2] and count (Z) at z0+1. */
 int hdn_window_accumulate(const float* logits, float* score, int* count, int S, int64_t HW,

@@ -41,7 +41,7 @@ class Case(object):
     output window inside a wider buffer."""
 
     def __init__(self, dev, N, D, H, W, cin, cout, k, ups=((1, 1, 1),), fold=(True,), bias=False, stats=False,
-                 drop=0.0, src_pad=16, out_pad=32, seed=0, stride=(1, 1, 1), src_c=None, tc=1):
+                 drop=0.0, src_pad=16, out_pad=32, seed=0, stride=(1, 1, 1), src_c=None, tc=1, device_fill=False):
         rng = np.random.default_rng(seed)
         self.net = net = engine.Net(engine.ParamStore(seed), dev, True, TC_NAME[tc], dropout=drop > 0)
         srcs = []
@@ -63,12 +63,20 @@ class Case(object):
         self.op = [o for o in net.ops if isinstance(o, engine.ConvOp)][0]
         _rand_fold_params(net.params, rng)
         net.compile()
-        g = torch.Generator(device="cpu").manual_seed(seed + 1)
-        for b in self.src_bufs:
-            b.data.copy_(torch.randn(b.data.shape, generator=g))
-            b.ensure_grad().zero_()
-        ob.data.zero_()
-        ob.ensure_grad().copy_(torch.randn(ob.data.shape, generator=g))
+        if device_fill:                       # headline-size tensors: draw on the device (1.6e9 host normals take minutes)
+            g = torch.Generator(device=dev).manual_seed(seed + 1)
+            for b in self.src_bufs:
+                b.data.normal_(generator=g)
+                b.ensure_grad().zero_()
+            ob.data.zero_()
+            ob.ensure_grad().normal_(generator=g)
+        else:
+            g = torch.Generator(device="cpu").manual_seed(seed + 1)
+            for b in self.src_bufs:
+                b.data.copy_(torch.randn(b.data.shape, generator=g))
+                b.ensure_grad().zero_()
+            ob.data.zero_()
+            ob.ensure_grad().copy_(torch.randn(ob.data.shape, generator=g))
         for f in net.folds:
             f.forward()
         self.supported = tuple(self.op.prec)

@@ -45,7 +45,7 @@ struct Wg2Params {
   int kd, kh, kw;
   int Cin, Cout;
   int BN, G, groups, ci_tiles, co_tiles;
-  int flat, layout;
+  int flat, layout, order;
   int PH, PW;
   int unitA, boxA, nunitA_max;        // stride / TMA box bytes of one A unit (plane or 64-channel block); units per stage
   int cwA;                            // channels per A unit
@@ -183,15 +183,32 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
         const uint8_t* sA = smem + (size_t)st * p.stage_bytes;
         const uint64_t ad0 = adesc_hi | (uint64_t)((tc::smem_u32(sA) >> 4) & 0x3FFF);
         const uint64_t bd0 = bdesc_hi | (uint64_t)((tc::smem_u32(sA + p.offB) >> 4) & 0x3FFF);
-        uint32_t tap_units = tap_units0;
-        int twc = twc0;
-        uint32_t tm = tmem_base;
-        for (int g = 0; g < p.G; ++g, tm += (uint32_t)p.BN) {
-          const uint64_t ad = ad0 + tap_units;
-          tc::umma_bf16(tm, ad, bd0, idesc, acc);
+        if (p.order == 0) {
+          // tap-major: the 8 K steps of a tap back to back (a dependent chain on one accumulator)
+          uint32_t tap_units = tap_units0;
+          int twc = twc0;
+          uint32_t tm = tmem_base;
+          for (int g = 0; g < p.G; ++g, tm += (uint32_t)p.BN) {
+            const uint64_t ad = ad0 + tap_units;
+            tc::umma_bf16(tm, ad, bd0, idesc, acc);
 #pragma unroll
-          for (int r = 1; r < 8; ++r) tc::umma_bf16(tm, ad + (uint64_t)(r * row2), bd0 + (uint64_t)(r * 16), idesc, 1u);
-          if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1) * pixu; } else tap_units += pixu;
+            for (int r = 1; r < 8; ++r) tc::umma_bf16(tm, ad + (uint64_t)(r * row2), bd0 + (uint64_t)(r * 16), idesc, 1u);
+            if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1) * pixu; } else tap_units += pixu;
+          }
+        } else {
+          // K-step-major: consecutive MMAs go to DIFFERENT accumulators (one per tap), so an MMA never waits for the
+          // accumulation of the one issued just before it; the dY descriptor is shared by the G MMAs of a K step
+          for (int r = 0; r < 8; ++r) {
+            uint32_t tap_units = tap_units0;
+            int twc = twc0;
+            uint32_t tm = tmem_base;
+            const uint64_t adr = ad0 + (uint64_t)(r * row2), bdr = bd0 + (uint64_t)(r * 16);
+            const uint32_t a2 = r ? 1u : acc;
+            for (int g = 0; g < p.G; ++g, tm += (uint32_t)p.BN) {
+              tc::umma_bf16(tm, adr + tap_units, bdr, idesc, a2);
+              if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1) * pixu; } else tap_units += pixu;
+            }
+          }
         }
         acc = 1;
         tc::umma_commit(&empty[st]);
@@ -506,6 +523,7 @@ int hdn_conv_wgrad_tc2(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.Cin = c->Cin; p.Cout = c->Cout;
   p.BN = pl.BN; p.G = pl.G; p.groups = pl.groups; p.ci_tiles = pl.ci_tiles; p.co_tiles = pl.co_tiles;
   p.flat = pl.flat; p.layout = pl.layout; p.PH = pl.PH; p.PW = pl.PW;
+  { const char* e = getenv("HDN_TC2_ORDER"); p.order = e ? atoi(e) : 1; }
   p.unitA = pl.unitA; p.boxA = pl.boxA; p.nunitA_max = pl.nunitA_max; p.cwA = pl.cwA;
   p.stage_bytes = pl.stage_bytes; p.offB = pl.offB; p.NS = pl.NS;
   p.pd_lo = c->kd / 2; p.ph_lo = c->kh / 2; p.pw_lo = c->kw / 2;

@@ -69,6 +69,7 @@ class Model(object):
         self.run_seed = int(os.environ.get("HDN_RUN_SEED", "0"))
         self._staging = {}
         self._staging_ev = {}
+        self._staging_used = {}
         self._copy_stream = None
         # register every parameter (host values, Keras default initialisers) without touching a device
         self._build(engine.Net(self.params, "meta", True, "fp32", backend=object(), dropout=False))
@@ -107,6 +108,9 @@ class Model(object):
                 net.seed_salt = (self.run_seed * 0x9E3779B1 + (rank + 1) * 0x85EBCA77) & 0xFFFFFFFF
                 net.step = self.global_step
             net.compile()
+            if getattr(self, "_pending_moms", None) is not None and len(self._pending_moms) == self.params.n_train:
+                self.params.moms[:self.params.n_train].copy_(torch.from_numpy(self._pending_moms))   # optimizer state of a loaded checkpoint
+                self._pending_moms = None
             self.nets[training] = net
         return net
 
@@ -156,6 +160,9 @@ class Model(object):
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(self._copy_stream):
+                used = self._staging_used.get(key)
+                if used is not None:
+                    self._copy_stream.wait_event(used)     # the compute stream's last reader of this device staging buffer is done
                 st[1].copy_(st[0], non_blocking=True)
                 if ev is None:
                     ev = self._staging_ev[key] = torch.cuda.Event()
@@ -181,6 +188,11 @@ class Model(object):
             dst[:, 0, :, :, :shape[-1]].copy_(src)
         else:
             dst.view(shape).copy_(src)
+        if dev.type == "cuda":
+            used = self._staging_used.get(key)
+            if used is None:
+                used = self._staging_used[key] = torch.cuda.Event()
+            used.record()
 
     def _h2d(self, x, dst, three_d):
         """host (reference layout) -> device NDHWC through the staging slots (see _stage / _unstage)."""
@@ -273,7 +285,9 @@ class Model(object):
 
     def fit_generator(self, generator, steps_per_epoch, epochs=1, verbose=1, callbacks=None, max_queue_size=10,
                       workers=1, use_multiprocessing=False, initial_epoch=0, **kwargs):
-        callbacks = callbacks or []
+        callbacks = list(callbacks or [])
+        if verbose and not any(isinstance(cb, LossHistory) for cb in callbacks):
+            callbacks.append(LossHistory())
         history = {"loss": []}
         for cb in callbacks:
             if hasattr(cb, "set_model"):
@@ -351,41 +365,125 @@ class Model(object):
         if self.dp is not None and self.dp.ready:
             self.dp._sync_initial(self.params)      # replicas stay identical: rank 0's values win (a collective call)
 
-    def save_weights(self, path, overwrite=True):
-        np.savez(path if path.endswith(".npz") else path + ".npz", **self.get_weights_dict())
+    @staticmethod
+    def _is_h5(path):
+        return path.endswith((".h5", ".hdf5", ".hdf"))
 
-    save = save_weights
+    def _optimizer_state(self):
+        if not self.params.realised:
+            return {"training/SGD/iterations:0": np.asarray(self.global_step, np.int64)}
+        return {"training/SGD/iterations:0": np.asarray(self.global_step, np.int64),
+                "training/SGD/momentum_arena:0": self.params.moms[:self.params.n_train].detach().cpu().numpy()}
+
+    def save_weights(self, path, overwrite=True):
+        """topology.py:2555-2590: a Keras-layout HDF5 file for *.h5 / *.hdf5 paths (keras_h5.write), else the npz container."""
+        if not overwrite and os.path.isfile(path):
+            raise IOError("%s exists and overwrite=False" % path)
+        if self._is_h5(path):
+            from . import keras_h5
+            keras_h5.write(path, self.get_weights_dict())
+        else:
+            np.savez(path if path.endswith(".npz") else path + ".npz", **self.get_weights_dict())
+
+    def save(self, path, overwrite=True, include_optimizer=True):
+        """models.py:56-130 `save_model`: weights under `model_weights` plus the optimizer state (momentum arena and the
+        step counter) under `optimizer_weights`, which is what ModelCheckpoint(save_weights_only=False) writes."""
+        if not overwrite and os.path.isfile(path):
+            raise IOError("%s exists and overwrite=False" % path)
+        opt = self._optimizer_state() if include_optimizer else None
+        if self._is_h5(path):
+            from . import keras_h5
+            keras_h5.write(path, self.get_weights_dict(), full=True, optimizer=opt)
+        else:
+            d = dict(self.get_weights_dict())
+            if opt:
+                d.update({"__optimizer__/" + k: v for k, v in opt.items()})
+            np.savez(path if path.endswith(".npz") else path + ".npz", **d)
+
+    def _restore_optimizer(self, opt):
+        it = opt.get("training/SGD/iterations:0")
+        if it is not None:
+            self.global_step = int(np.asarray(it))
+            for net in self.nets.values():
+                net.step = self.global_step
+        m = opt.get("training/SGD/momentum_arena:0")
+        if m is not None and self.params.realised and len(m) == self.params.n_train:
+            self.params.moms[:self.params.n_train].copy_(torch.from_numpy(np.asarray(m, np.float32)))
+        elif m is not None:
+            self._pending_moms = np.asarray(m, np.float32)
 
     def load_weights(self, path, by_name=False, by_gpu=False, two_model=False, by_flag=False):
-        """topology.py:2590.  .npz written by save_weights; by_name ignores unknown / missing entries.
-        Keras HDF5 files (incl. the by_gpu / two_model / by_flag variants, topology.py:3171-3330)
-        need the HDF5 reader listed as the first 'next' row of SURVEY.md 8(f)."""
-        if path.endswith((".h5", ".hdf5")):
-            raise NotImplementedError("Keras HDF5 weight files are not readable yet (SURVEY.md 8f rank 1); "
-                                      "use the .npz written by save_weights")
-        with np.load(path if path.endswith(".npz") else path + ".npz") as z:
-            self.set_weights_dict({k: z[k] for k in z.files}, strict=not by_name)
+        """topology.py:2590-2630 incl. the reference's by_gpu / two_model / by_flag loaders (keras_h5.read).  A path
+        that does not exist falls back to `<path>.npz` (the container of round 1's checkpoints)."""
+        if self._is_h5(path) and os.path.isfile(path):
+            from . import keras_h5
+            got, info = keras_h5.read(path, [p.name for p in self.params.order], by_name=by_name, by_gpu=by_gpu,
+                                      two_model=two_model, by_flag=by_flag)
+            self.set_weights_dict(got, strict=True)
+            if info.get("optimizer"):
+                self._restore_optimizer(info["optimizer"])
+            return
+        npz = path if path.endswith(".npz") else path + ".npz"
+        if not os.path.isfile(npz):
+            raise IOError("Unable to open file (no such file: %s)" % path)
+        with np.load(npz) as z:
+            self.set_weights_dict({k: z[k] for k in z.files if not k.startswith("__optimizer__/")}, strict=not by_name)
+            opt = {k[len("__optimizer__/"):]: z[k] for k in z.files if k.startswith("__optimizer__/")}
+        if opt:
+            self._restore_optimizer(opt)
 
     def count_params(self):
         return sum(p.size for p in self.params.order)
 
 
 class ModelCheckpoint(object):
-    """callbacks.py:335-432 (filename template with {epoch} / {loss}); writes the npz container."""
+    """callbacks.py:335-432: `filepath.format(epoch=epoch, **logs)` with the 0-based epoch (callbacks.py:404), every
+    `period` epochs; save_weights_only=False (what the three scripts pass) saves the full model incl. optimizer state."""
 
     def __init__(self, filepath, monitor="loss", verbose=0, save_best_only=False, save_weights_only=False,
                  mode="auto", period=1):
-        self.filepath, self.verbose, self.period, self.model = filepath, verbose, period, None
+        self.filepath, self.monitor, self.verbose, self.period, self.model = filepath, monitor, verbose, period, None
+        self.save_best_only, self.save_weights_only = save_best_only, save_weights_only
+        self.epochs_since_last_save = 0
+        self.best = -np.inf if mode == "max" else np.inf
+        self.better = np.greater if mode == "max" else np.less
 
     def set_model(self, model):
         self.model = model
 
     def on_epoch_end(self, epoch, logs=None):
-        if (epoch + 1) % self.period == 0:
-            path = self.filepath.format(epoch=epoch + 1, **(logs or {}))
-            self.model.save_weights(path)
-            if self.verbose:
-                print("Epoch %05d: saving model to %s" % (epoch + 1, path))
+        logs = logs or {}
+        self.epochs_since_last_save += 1
+        if self.epochs_since_last_save < self.period:
+            return
+        self.epochs_since_last_save = 0
+        path = self.filepath.format(epoch=epoch, **logs)
+        if self.save_best_only:
+            cur = logs.get(self.monitor)
+            if cur is None or not self.better(cur, self.best):
+                return
+            self.best = cur
+        if self.verbose:
+            print("Epoch %05d: saving model to %s" % (epoch, path))
+        if self.save_weights_only:
+            self.model.save_weights(path, overwrite=True)
+        else:
+            self.model.save(path, overwrite=True)
+
+
+class LossHistory(object):
+    """The reference's ProgbarLogger edit (callbacks.py:311-314): append '%.4f' of the epoch loss to
+    <path>/history/lossepoch.txt, path = './Experiments/' (callbacks.py:28).  fit_generator installs it when verbose
+    and the directory exists (the reference crashes when it does not)."""
+
+    def __init__(self, path=None):
+        self.path = path or os.environ.get("HDN_EXPERIMENTS_PATH", "./Experiments/")
+
+    def on_epoch_end(self, epoch, logs=None):
+        d = os.path.join(self.path, "history")
+        if os.path.isdir(d) and logs and "loss" in logs:
+            with open(os.path.join(d, "lossepoch.txt"), "a") as fh:
+                fh.write("%.4f\n" % logs["loss"])
 
 
 def make_parallel(model, gpu_count, mini_batch=None):

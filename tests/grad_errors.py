@@ -18,13 +18,16 @@ from oracle import hdense_oracle as orc  # noqa: E402
 from util import Args, perturb_params, rel_l2, synthetic_slab  # noqa: E402
 
 
+SIZE = int(os.environ.get("HDN_GE_SIZE", "64"))
+
+
 def run(prec, oracle):
-    a = Args(b=1, input_size=64, input_cols=8)
+    a = Args(b=1, input_size=SIZE, input_cols=8)
     m = hdn.dense_rnn_net(a, precision=prec)
     m.dropout = False
     perturb_params(m)
     m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
-    vol, lab = synthetic_slab(1, 64, 8)
+    vol, lab = synthetic_slab(1, SIZE, 8)
     if not oracle:
         w0 = m.get_weights_dict()
         for dt in (torch.float32, torch.float64):
@@ -46,7 +49,13 @@ def run(prec, oracle):
     return {"precision": prec, "logits_rel_l2": rel_l2(m._logits_to_host(net), lg32), "loss": got, "loss_oracle": l32,
             "loss_rel": abs(got - l32) / abs(l32), "n_tensors": len(errs), "grad_max": float(e.max()),
             "grad_median": float(np.median(e)), "grad_over_5e-3": int((e > 5e-3).sum()), "grad_over_1e-2": int((e > 1e-2).sum()),
-            "worst": [(k, round(a_, 5), round(b_, 5)) for a_, b_, k in errs[:8]],
+            "size": SIZE, "grad_over_1e-3": int((e > 1e-3).sum()),
+            "by_family": {fam: [round(float(np.median([x[0] for x in errs if x[2].startswith(fam)])), 5),
+                                round(float(max([x[0] for x in errs if x[2].startswith(fam)])), 5)]
+                          for fam in ("conv1", "conv2_", "conv3_", "conv4_", "conv5_", "conv_up", "bn_up", "dense167", "3dconv1", "3dconv2_",
+                                      "3dconv3_", "3dconv4_", "3dconv5_", "3dconv_up", "3dbn_up", "fianl", "final_bn", "2d3d")
+                          if any(x[2].startswith(fam) for x in errs)},
+            "worst": [(k, round(a_, 5), round(b_, 5)) for a_, b_, k in errs[:int(os.environ.get("HDN_GE_WORST", "8"))]],
             "passes": sorted(set(p for _, p in net.report))}
 
 

@@ -11,8 +11,15 @@ numpy inputs (pinned staging + H2D inside the timed region, loss read back every
 
 The reference's arithmetic is TensorFlow-1.x, which cannot be installed here, so the reference arm
 and the `cpu_baseline` both time the oracle's PyTorch-CPU restatement of the reference graph (kind "port") on a
-bounded sample: one (1, 160, 160, 8) slab (the reference trains on 224x224x8, train_hybrid.py:28-31), scaled to
-512x512x48-slab units by voxel count.
+bounded sample: one (1, 224, 224, 8) slab -- the reference's own training shape (train_hybrid.py:28-31) -- scaled to
+512x512x48-slab units by voxel count; median of >= 5 timed steps after one warm-up step, same thread count in both legs.
+
+--config selects the BASELINE.json configuration (default c4, the headline; the others are kept under profiles/):
+    c2  2-D DenseUNet-161 train step (train_2ddense.py), batch 8 x 512x512, training-mode BN + Dropout(.3)
+    c3  3-D DenseNet + head fwd+bwd on one 224x224x12 sub-volume (hybridnet.py:98-178)
+    c4  H-DenseUNet end2end train step, 512x512x48 slabs, batch 2 per GPU, data parallel 1 -> 8 GPUs
+    c5  sliding-window inference of one 512x512x512 volume (test.py / lib/funcs.py:4-51), 253 windows, z-sharded over
+        the GPUs, with and without 2-D slice reuse
 """
 import argparse
 import json
@@ -29,8 +36,15 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "CT slabs/sec (512x512x48) fwd+bwd"
 FULL_VOXELS = 512 * 512 * 48
+
+# BASELINE.json configs: metric, unit of one "work unit", model kind
+CONFIGS = {
+    "c2": {"metric": "2D slices/sec (512x512) DenseUNet-161 train step", "unit": "slices/s"},
+    "c3": {"metric": "3D sub-volumes/sec (224x224x12) DenseNet3D fwd+bwd", "unit": "subvolumes/s"},
+    "c4": {"metric": "CT slabs/sec (512x512x48) fwd+bwd", "unit": "slabs/s"},
+    "c5": {"metric": "CT volumes/sec (512x512x512) sliding-window inference", "unit": "volumes/s"},
+}
 
 
 class Args(object):
@@ -93,31 +107,132 @@ class ClockSampler(object):
                 "samples": len(sm), "sm_min_mhz": float(min(sm)), "power_w_max": float(max(pw)) if pw else None}
 
 
-# --------------------------------------------------------------------------------- CPU arm
-def cpu_step_fn(size, cols, threads):
-    """Returns (fn, sample description): fn() runs one fwd+loss+bwd+SGD of the oracle on one slab."""
-    from oracle import hdense_oracle as orc
+# --------------------------------------------------------------------------------- workloads
+def defaults(a):
+    """Shape defaults per config (flags override): (batch per GPU, size, cols)."""
+    d = {"c2": (8, 512, None), "c3": (1, 224, 12), "c4": (2, 512, 48), "c5": (1, 512, 8)}[a.config]
+    a.batch = d[0] if a.batch is None else a.batch
+    a.size = d[1] if a.size is None else a.size
+    a.cols = d[2] if a.cols is None else a.cols
+    # CPU sample of the same workload: the reference's own training shapes (train_hybrid.py:28-31, train_2ddense.py:27)
+    a.cpu_size = a.cpu_size or 224
+    a.cpu_cols = a.cpu_cols or (12 if a.config == "c3" else 8)
+    return a
+
+
+def build_model(a, precision, seed=0, **kw):
     import h_denseunet_b200 as hdn
+    if a.config == "c2":
+        return hdn.DenseUNet(reduction=0.5, args=Args(a.batch, a.size, None), precision=precision, seed=seed, **kw)
+    if a.config == "c3":
+        return hdn.DenseNet3D(Args(a.batch, a.size, a.cols), precision=precision, seed=seed, **kw)
+    return hdn.dense_rnn_net(Args(a.batch, a.size, a.cols), precision=precision, seed=seed, **kw)
+
+
+def host_batch(a, rank):
+    """Synthetic host arrays in the reference's layouts."""
+    from h_denseunet_b200.synthetic import synthetic_slab
+    if a.config == "c2":
+        vol, lab = synthetic_slab(1, a.size, max(a.batch + 2, 4), seed=1234 + rank)      # slices of one synthetic volume
+        v = vol[0, :, :, :, 0]
+        x = np.stack([v[:, :, i:i + 3] for i in range(a.batch)]).astype(np.float32)      # (b, H, W, 3) slice triplets
+        y = np.stack([lab[0, :, :, i + 1, :] for i in range(a.batch)]).astype(np.int16)  # (b, H, W, 1)
+        return x, y
+    vol, lab = synthetic_slab(a.batch, a.size, a.cols, seed=1234 + rank)
+    if a.config == "c3":
+        rng = np.random.default_rng(7 + rank)
+        x = np.concatenate([vol, rng.normal(0, 50, vol.shape[:-1] + (3,)).astype(np.float32)], axis=-1)   # [CT, 250*logits2d]
+        return x, lab
+    return vol, lab
+
+
+def units_per_step(a, world):
+    if a.config == "c2":
+        return a.batch * world * (a.size * a.size) / float(512 * 512)
+    if a.config == "c3":
+        return a.batch * world * (a.size * a.size * a.cols) / float(224 * 224 * 12)
+    return a.batch * world * (a.size * a.size * a.cols) / float(FULL_VOXELS)
+
+
+def loss_of(a):
+    import h_denseunet_b200 as hdn
+    return hdn.weighted_crossentropy_2ddense if a.config == "c2" else hdn.weighted_crossentropy
+
+
+# --------------------------------------------------------------------------------- CPU arm
+def cpu_step_fn(a, threads):
+    """Returns (fn, sample description, units per call): fn() runs the oracle on a bounded sample of the workload."""
+    from oracle import hdense_oracle as orc
     from h_denseunet_b200.synthetic import synthetic_slab
     torch.set_num_threads(threads)
-    m = hdn.dense_rnn_net(Args(1, size, cols))          # parameter dictionary only; no device is touched
+    size, cols = a.cpu_size, a.cpu_cols
+    ca = argparse.Namespace(**vars(a))
+    ca.size, ca.cols, ca.batch = size, cols, 1
+    m = build_model(ca, "fp32", backend=object(), device="cpu")          # parameter dictionary only; no device is touched
     w = m.get_weights_dict()
-    vol, lab = synthetic_slab(1, size, cols)
     mom = {}
 
-    def fn():
-        ctx, logits = orc.forward_hybrid(w, vol, training=True, variant="end2end", requires_grad=True)
-        loss = orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), logits, crop=True)
-        g = orc.grads_of(ctx, loss)
+    def sgd(g):
         for k, gk in g.items():
             if gk is None:
                 continue
             p1, v = orc.sgd_nesterov_step(w[k], gk, mom.get(k, 0.0))
             w[k], mom[k] = p1.astype(np.float32), v
+
+    if a.config == "c2":
+        x, y = host_batch(ca, 0)
+
+        def fn():
+            ctx, _, logits = orc.forward_2d(w, x, training=True, learn_bn=True, requires_grad=True)
+            loss = orc.weighted_crossentropy(torch.as_tensor(y), logits, crop=False)
+            sgd(orc.grads_of(ctx, loss))
+            return float(loss.detach())
+        return fn, "1 slice (1,%d,%d,3) fwd+bwd+SGD, torch-CPU fp32 oracle, scaled by pixel count to 512x512" % (size, size), \
+            size * size / float(512 * 512)
+    if a.config == "c3":
+        x, y = host_batch(ca, 0)
+
+        def fn():
+            ctx, feat = orc.forward_3d(w, x, training=True, requires_grad=True)
+            loss = (feat * feat).mean()                    # the head (one 3x3x3 + one 1x1x1 conv of ~60) is < 12 % of the FLOPs
+            orc.grads_of(ctx, loss)
+            return float(loss.detach())
+        return fn, "1 sub-volume (1,%d,%d,%d,4) 3-D DenseNet fwd+bwd, torch-CPU fp32 oracle, scaled by voxel count to 224x224x12" % (
+            size, size, cols), size * size * cols / float(224 * 224 * 12)
+    vol, lab = synthetic_slab(1, size, cols)
+    if a.config == "c5":
+        def fn():
+            with torch.no_grad():
+                _, logits = orc.forward_hybrid(w, vol, training=False, variant="end2end")
+            return float(logits.mean())
+        nwin = 253.0
+        return fn, "1 window (1,%d,%d,%d,1) forward, torch-CPU fp32 oracle, scaled by voxel count to 512x512x8 and by the 253 " \
+                   "windows of a 512-slice volume" % (size, size, cols), size * size * cols / float(512 * 512 * 8) / nwin
+
+    def fn():
+        ctx, logits = orc.forward_hybrid(w, vol, training=True, variant="end2end", requires_grad=True)
+        loss = orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), logits, crop=True)
+        sgd(orc.grads_of(ctx, loss))
         return float(loss.detach())
 
     return fn, "1 slab (1,%d,%d,%d,1) fwd+bwd+SGD, torch-CPU fp32 oracle, scaled by voxel count to 512x512x48" % (
-        size, size, cols)
+        size, size, cols), size * size * cols / float(FULL_VOXELS)
+
+
+def cpu_measure(a, threads, reps, budget_s=None):
+    """One untimed warm-up call, then `reps` timed calls (fewer if `budget_s` runs out, never fewer than 1): median."""
+    fn, sample, units = cpu_step_fn(a, threads)
+    out = fn()
+    ts = []
+    t_all = time.perf_counter()
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out = fn()
+        ts.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_all > budget_s:
+            break
+    dt = float(np.median(ts))
+    return units / dt, dt, sample, len(ts), out
 
 
 def run_reference(a):
@@ -125,25 +240,16 @@ def run_reference(a):
     if rank != 0:
         return
     threads = min(os.cpu_count() or 1, a.cpu_threads)
-    size, cols = a.cpu_size, a.cpu_cols
-    fn, sample = cpu_step_fn(size, cols, threads)
-    warm, _ = cpu_step_fn(32, 8, threads)                   # untimed warm-up on a tiny slab
-    for _ in range(max(min(a.warmup, 1), 0)):
-        warm()
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        loss = fn()
-    dt = (time.perf_counter() - t0) / a.steps
-    slabs = (size * size * cols) / float(FULL_VOXELS)
-    v = slabs / dt
+    v, dt, sample, n, out = cpu_measure(a, threads, max(a.steps, 1))
+    cfg = CONFIGS[a.config]
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "slabs/s", "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": cfg["metric"], "value": v, "unit": cfg["unit"], "n_gpus": a.gpus, "steps": n,
+        "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "hybrid end2end train step (hybridnet.dense_rnn_net), CPU sample %dx%dx%d" % (size, size, cols)},
-        "cpu_baseline": {"value": v, "unit": "slabs/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "slabs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "loss": loss}))
+        "config": {"workload": "%s, CPU sample %dx%dx%s" % (a.config, a.cpu_size, a.cpu_size, a.cpu_cols), "statistic": "median of %d" % n},
+        "cpu_baseline": {"value": v, "unit": cfg["unit"], "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "loss": out}))
 
 
 # --------------------------------------------------------------------------------- GPU arm
@@ -213,9 +319,35 @@ def profile_step(model, net, steps):
     return agg, ops, gaps
 
 
-def run_gpu(a):
-    import h_denseunet_b200 as hdn
-    from h_denseunet_b200.synthetic import synthetic_slab
+WORKLOAD_TEXT = {
+    "c2": "2-D DenseUNet-161 train step (densenet.DenseUNet, train_2ddense.py): %(batch)d slice(s)/GPU of %(size)dx%(size)d, training-mode "
+          "BN, fwd + weighted CE + bwd + Nesterov SGD",
+    "c3": "3-D DenseNet + hybrid head (hybridnet.DenseNet3D): %(batch)d sub-volume(s)/GPU of %(size)dx%(size)dx%(cols)d x 4 channels, "
+          "fwd + weighted CE + bwd + Nesterov SGD",
+    "c4": "H-DenseUNet end2end train step (hybridnet.dense_rnn_net): %(batch)d slab(s)/GPU of %(size)dx%(size)dx%(cols)d, "
+          "fwd + weighted CE + bwd + Nesterov SGD",
+}
+
+
+def load_peaks():
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        with open(pk) as f:
+            return json.load(f)
+    return {}
+
+
+def load_traffic():
+    """ncu DRAM bytes per launch of the dominant kernels (profiles/r02_traffic.json, written by scripts/ncu_digest.py
+    from `ncu --set full` captures of this round's kernels at the headline shape)."""
+    tj = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tj):
+        with open(tj) as f:
+            return json.load(f)
+    return {}
+
+
+def dist_setup(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,24 +361,26 @@ def run_gpu(a):
         dist.init_process_group("nccl", device_id=dev)
     if world != a.gpus:
         raise RuntimeError("--gpus %d but WORLD_SIZE is %d (launch with torch.distributed.run)" % (a.gpus, world))
+    return world, rank, local, dev, dist
 
-    peaks = {}
-    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(pk):
-        with open(pk) as f:
-            peaks = json.load(f)
 
-    m = hdn.dense_rnn_net(Args(a.batch, a.size, a.cols), precision=a.precision, seed=0)
+def run_gpu(a):
+    import h_denseunet_b200 as hdn
+    world, rank, local, dev, dist = dist_setup(a)
+    peaks = load_peaks()
+    cfg = CONFIGS[a.config]
+
+    m = build_model(a, a.precision, seed=0)
     m.dropout = not a.no_dropout
     if world > 1:
         hdn.make_parallel(m, world, mini_batch=a.batch)
-    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
-    vol, lab = synthetic_slab(a.batch, a.size, a.cols, seed=1234 + rank)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[loss_of(a)])
+    x, y = host_batch(a, rank)
     net = m._net(True)
     ntc = sum(1 for _, p in net.report if any(p))
 
     # device-resident arm: upload once, then time train_step_device
-    m.train_on_batch(vol, lab)
+    m.train_on_batch(x, y)
     for _ in range(max(a.warmup - 1, 0)):
         m.train_step_device(net)
     l0 = net.be.launches
@@ -254,27 +388,36 @@ def run_gpu(a):
         ms, loss = timed(lambda: m.train_step_device(net), a.steps, dist, dev)
     launches = (net.be.launches - l0) // a.steps
     clocks = clk.summary()
-    # end-to-end arm: host numpy in, loss out, every step
-    m.train_on_batch(vol, lab)
-    ms_e2e, loss_e2e = timed(lambda: m.train_on_batch(vol, lab), a.steps, dist, dev)
-    h2d = int(m.h2d_bytes)          # bytes Model.train_on_batch copied host -> device this step (fp32 volume + int16 label map)
 
-    slabs_step = a.batch * world * (a.size * a.size * a.cols) / float(FULL_VOXELS)
-    value = slabs_step / (ms * 1e-3)
-    e2e = slabs_step / (ms_e2e * 1e-3)
+    # end-to-end arm: the call the reference scripts make (train_hybrid.py:213, train_2ddense.py:209): fit_generator over a
+    # generator of HOST numpy batches.  Every step copies its batch host -> pinned -> device (on the copy stream, while the
+    # previous step computes) and reads the step's loss back; both inside the timed region.
+    def gen():
+        while True:
+            yield x, y
 
+    g = gen()
+    m.fit_generator(g, steps_per_epoch=2, epochs=1, verbose=0)                    # staging buffers / copy stream warm-up
+    ms_e2e, hist = timed(lambda: m.fit_generator(g, steps_per_epoch=a.steps, epochs=1, verbose=0), 1, dist, dev)
+    ms_e2e /= a.steps
+    h2d = int(m.h2d_bytes)          # bytes staged host -> device per step (fp32 volume + int16 label map)
+
+    units = units_per_step(a, world)
+    value = units / (ms * 1e-3)
+    e2e = units / (ms_e2e * 1e-3)
+    desc = dict(batch=a.batch, size=a.size, cols=a.cols or 0)
     line = {
-        "metric": METRIC, "value": value, "unit": "slabs/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "metric": cfg["metric"], "value": value, "unit": cfg["unit"], "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if a.precision in ("bf16", "bf16x3", "mixed") and ntc else "f32", "data": "synthetic",
-        "config": {"workload": "H-DenseUNet end2end train step (hybridnet.dense_rnn_net): %d slab(s)/GPU of %dx%dx%d, "
-                               "fwd + weighted CE + bwd + Nesterov SGD%s" % (
-                                   a.batch, a.size, a.size, a.cols, " + P2P grad reduce" if world > 1 else ""),
-                   "slab": [a.size, a.size, a.cols], "batch_per_gpu": a.batch, "parallelism": "dp%d" % world,
+        "config": {"workload": WORKLOAD_TEXT[a.config] % desc + (" + P2P grad reduce" if world > 1 else ""), "baseline_config": a.config,
+                   "shape": [a.size, a.size] + ([a.cols] if a.cols else []), "batch_per_gpu": a.batch, "parallelism": "dp%d" % world,
                    "precision": a.precision, "tc_convs": ntc, "convs": len(net.report), "dropout": m.dropout,
                    "l2": "activations per step (%.1f GiB) exceed the 126 MB L2; no flush needed" % (
-                       net.memory_bytes() / 2 ** 30)},
-        "e2e": {"value": e2e, "unit": "slabs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                       net.memory_bytes() / 2 ** 30),
+                   "e2e_call": "Model.fit_generator(host numpy generator): pinned staging + H2D on a copy stream, loss read back "
+                               "every step"},
+        "e2e": {"value": e2e, "unit": cfg["unit"], "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches), "clocks": clocks, "loss": loss, "memory_gib": net.memory_bytes() / 2 ** 30,
     }
@@ -294,15 +437,15 @@ def run_gpu(a):
             peak_tf = 148 * 128 * 2 * (clocks["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
         ach = fl / (t * 1e-3) / 1e12 if t > 0 else 0.0
         traffic, tsrc = None, None
-        tj = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tj):
-            with open(tj) as f:
-                tr = json.load(f)
-            what = k.split("[")[0].replace("conv_", "")
-            if opname in tr and what in tr[opname]:
-                traffic = tr[opname][what] * a.cols * a.batch
-                tsrc = tr["_source"]
-        line["roofline"] = {"kernel": "%s %s" % (k, opname), "bound": "tensor" if "[tc" in k else "fp32-fma", "achieved": ach,
+        tr = load_traffic()
+        key = "%s %s" % (k, opname)
+        if key in tr.get("per_launch", {}):
+            ent = tr["per_launch"][key]
+            if ent.get("positions"):                          # captured at the headline shape, or scaled by output positions (said so)
+                traffic = ent["dram_bytes"] * (units * FULL_VOXELS / world if a.config == "c4" else ent["positions"]) / ent["positions"] \
+                    if a.config == "c4" else None
+            tsrc = tr.get("_source")
+        line["roofline"] = {"kernel": key, "bound": "tensor" if "[tc" in k else "fp32-fma", "achieved": ach,
                             "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
                             "traffic": traffic, "traffic_source": tsrc, "ms_per_launch": t,
                             "share_of_step": t * n / tot if tot else None, "launches": n,
@@ -316,23 +459,83 @@ def run_gpu(a):
                                         "launches": v[2] // a.profile_steps,
                                         "hbm_gbs": round(v[3] / max(v[0], 1e-9) / 1e6, 1),
                                         "hbm_frac": round(v[3] / max(v[0], 1e-9) / 1e6 / hbm_peak, 4)}
-                                  for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:12]}
+                                  for kk, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:16]}
+        line["step_tflops"] = round(sum(v[1] for v in agg.values()) / a.profile_steps / (ms * 1e-3) / 1e12, 1)
         line["launch_gaps"] = gaps
-        # CPU baseline on this box's host cores, bounded sample
+        # CPU baseline on this box's host cores, bounded sample of the same workload (median of 5 after a warm-up)
         if not a.no_cpu:
             threads = min(os.cpu_count() or 1, a.cpu_threads)   # oneDNN convolutions of this size stop scaling past ~32 threads
-            fn, sample = cpu_step_fn(a.cpu_size, a.cpu_cols, threads)
-            warm, _ = cpu_step_fn(32, 8, threads)           # thread pools / allocator warm-up on a tiny slab, untimed
-            warm()
-            t0 = time.perf_counter()
-            n_rep = 0
-            while n_rep < 2 and (time.perf_counter() - t0) < 12.0:      # bounded: ~10-30 s of CPU work
-                fn()
-                n_rep += 1
-            dt = (time.perf_counter() - t0) / n_rep
-            v = (a.cpu_size * a.cpu_size * a.cpu_cols) / float(FULL_VOXELS) / dt
-            line["cpu_baseline"] = {"value": v, "unit": "slabs/s", "cores": threads, "kind": "port", "sample": sample,
-                                    "s_per_sample_step": dt}
+            v, dt, sample, nrep, _ = cpu_measure(a, threads, 5, budget_s=60.0)
+            line["cpu_baseline"] = {"value": v, "unit": cfg["unit"], "cores": threads, "kind": "port", "sample": sample,
+                                    "s_per_sample_step": dt, "statistic": "median of %d after 1 warm-up" % nrep}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------- config 5: sliding-window inference
+def run_c5(a):
+    """One synthetic 512x512xZ volume through predict_tumor_inwindow (lib/funcs.py:4-51 / test.py:48-69): full liver
+    mask => windows range(0, Z-6, 2) (253 for Z = 512), z-sharded over the ranks, one all-reduce of the accumulators.
+    A "step" is the whole volume.  `value` keeps the volume on the device side of the call as far as the API allows
+    (the window stack is cut from a host array, as in the reference); e2e == value's call: host volume in, two host
+    probability volumes out."""
+    import h_denseunet_b200 as hdn
+    from h_denseunet_b200 import inference
+    from h_denseunet_b200.synthetic import synthetic_slab
+    world, rank, local, dev, dist = dist_setup(a)
+    peaks = load_peaks()
+    cfg = CONFIGS["c5"]
+    Z = a.depth
+    vol, _ = synthetic_slab(1, a.size, Z, seed=1239)
+    imgs = np.ascontiguousarray(vol[0, :, :, :, 0])                       # (H, W, Z), as test.py hands it over
+    mini, maxi = np.array([0, 0, 0]), np.array([a.size - 1, a.size - 1, Z - 1])
+    args = Args(1, a.size, a.cols)
+    m = hdn.dense_rnn_net(args, precision=a.precision, seed=0)
+    out = {}
+    starts = inference.window_starts(Z, int(mini[2]), int(maxi[2]), a.cols)
+    fwd_tflop = 3.165 * (a.size / 512.0) ** 2 * (a.cols / 8.0)               # SURVEY.md 8d: 3.165 TFLOP per 512x512x8 window
+    f2d = 8.86 / 48.0 * (a.size / 512.0) ** 2                                # 2-D part per slice
+    for reuse in (False, True):
+        st = {}
+        for _ in range(max(a.warmup // 3, 1) if a.steps else 0):            # one untimed volume (programs, staging, clocks)
+            hdn.predict_tumor_inwindow(m, imgs, 3, mini, maxi, args, reuse_2d=reuse, stats=st)
+        t0 = time.perf_counter()
+        with ClockSampler(local) as clk:
+            ms, res = timed(lambda: hdn.predict_tumor_inwindow(m, imgs, 3, mini, maxi, args, reuse_2d=reuse, stats=st), a.steps, dist, dev)
+        wall = (time.perf_counter() - t0) / max(a.steps, 1)
+        nwin = len(starts)
+        naive = nwin * fwd_tflop
+        dedup = naive - (nwin * a.cols - st["slices_2d"] * world) * f2d if reuse else naive
+        out[reuse] = {"s_per_volume": ms * 1e-3, "wall_s_per_volume": wall, "volumes_per_s": 1e3 / ms, "windows": nwin,
+                      "windows_this_rank": st["windows"], "slices_2d_this_rank": st["slices_2d"],
+                      "tflop_naive": round(naive, 1), "tflop_evaluated": round(dedup, 1),
+                      "tflops_naive_rate": round(naive / (ms * 1e-3), 1), "clocks": clk.summary(),
+                      "checksum": [float(res[0].sum()), float(res[1].sum())]}
+    if rank == 0:
+        best = out[True] if out[True]["s_per_volume"] < out[False]["s_per_volume"] else out[False]
+        line = {"metric": cfg["metric"], "value": best["volumes_per_s"], "unit": cfg["unit"], "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": best["s_per_volume"] * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16" if a.precision != "fp32" else "f32", "data": "synthetic",
+                "config": {"workload": "sliding-window inference of one %dx%dx%d volume (lib/funcs.py:4-51): %d windows of %d slices, "
+                                       "stride %d, z-sharded over %d GPU(s)" % (a.size, a.size, Z, len(starts), a.cols, a.cols // 4, world),
+                           "baseline_config": "c5", "precision": a.precision, "parallelism": "z%d" % world,
+                           "l2": "one window's activations (>3 GiB) exceed the 126 MB L2; no flush needed"},
+                "e2e": {"value": best["volumes_per_s"], "unit": cfg["unit"], "ms_per_step": best["s_per_volume"] * 1e3,
+                        "h2d_bytes_per_step": int(len(starts) / world * a.size * a.size * a.cols * 4),
+                        "d2h_bytes_per_step": int(a.size * a.size * Z * 2 * 4)},
+                "without_slice_reuse": out[False], "with_slice_reuse": out[True],
+                "gpu_launches": None, "clocks": best["clocks"]}
+        sustained = peaks.get("bf16_tflops_sustained") or 1400.0
+        line["roofline"] = {"kernel": "whole window forward (231 convolutions)", "bound": "tensor", "achieved": best["tflops_naive_rate"] / world,
+                            "peak": sustained, "unit": "TFLOP/s", "frac": best["tflops_naive_rate"] / world / sustained, "traffic": None,
+                            "note": "algorithmic (naive, direct-convolution) TFLOP of all windows / wall time, per GPU"}
+        if not a.no_cpu:
+            threads = min(os.cpu_count() or 1, a.cpu_threads)
+            v, dt, sample, nrep, _ = cpu_measure(a, threads, 5, budget_s=60.0)
+            line["cpu_baseline"] = {"value": v * (512.0 / Z), "unit": cfg["unit"], "cores": threads, "kind": "port", "sample": sample,
+                                    "s_per_sample_step": dt, "statistic": "median of %d after 1 warm-up" % nrep}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
@@ -345,21 +548,25 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--cols", type=int, default=48)
-    ap.add_argument("--batch", type=int, default=2, help="slabs per GPU (north star: 2)")
+    ap.add_argument("--config", default="c4", choices=["c2", "c3", "c4", "c5"], help="BASELINE.json configuration (default: the headline c4)")
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--cols", type=int, default=None)
+    ap.add_argument("--depth", type=int, default=512, help="c5: slices of the volume")
+    ap.add_argument("--batch", type=int, default=None, help="work units per GPU (c4 north star: 2 slabs; c2: 8 slices)")
     ap.add_argument("--precision", default="mixed", choices=["bf16", "bf16x3", "mixed", "fp32"],
                     help="bf16: tcgen05, operands rounded to bf16; bf16x3: tcgen05, operands split into bf16 head + tail "
                          "(3 MMAs per step, fp32-grade results); mixed: fprop + dgrad bf16x3, wgrad bf16; fp32: FMA parity path")
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=1)
-    ap.add_argument("--cpu-size", type=int, default=160)
-    ap.add_argument("--cpu-cols", type=int, default=8)
+    ap.add_argument("--cpu-size", type=int, default=None)
+    ap.add_argument("--cpu-cols", type=int, default=None)
     ap.add_argument("--cpu-threads", type=int, default=32, help="host threads of the CPU arm (capped at the core count)")
-    a = ap.parse_args()
+    a = defaults(ap.parse_args())
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == "c5":
+        run_c5(a)
     else:
         run_gpu(a)
 

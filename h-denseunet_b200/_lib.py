@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhdn.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc2_wgrad.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc2_wgrad.cu", "elementwise.cu", "postproc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -93,6 +93,7 @@ EXPORTS = [
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
     "hdn_window_accumulate", "hdn_window_finalize", "hdn_dev_malloc", "hdn_dev_free",
     "hdn_ipc_get_handle", "hdn_ipc_open", "hdn_ipc_close", "hdn_set_switch", "hdn_dp_signal", "hdn_dp_wait", "hdn_layout_nhws_to_nshw",
+    "hdn_post_threshold", "hdn_post_dilate", "hdn_post_largest_component", "hdn_post_fill_holes", "hdn_post_and", "hdn_post_compose",
 ]
 
 _lib = None
@@ -144,6 +145,12 @@ def load():
         "hdn_dp_signal": [vp, i32, i32, C.c_uint32, vp],
         "hdn_dp_wait": [vp, i32, C.c_uint32, vp],
         "hdn_layout_nhws_to_nshw": [vp, vp, i32, i32, i32, i32, i32, vp],
+        "hdn_post_threshold": [vp, vp, vp, vp, i64, f32, f32, vp],
+        "hdn_post_dilate": [vp, vp, i32, i32, i32, vp],
+        "hdn_post_largest_component": [vp, vp, i32, i32, i32, vp, i64, vp],
+        "hdn_post_fill_holes": [vp, vp, i32, i32, i32, vp, i64, vp],
+        "hdn_post_and": [vp, vp, vp, i64, vp],
+        "hdn_post_compose": [vp, vp, vp, i64, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -82,6 +82,7 @@ struct TcParams {
   int l2pf;                   // 1: raw patch copies carry the L2::256B prefetch hint (HDN_TC_L2PF, experiment)
   int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
+  int tail16;                 // 1: the tails of both operands are IEEE half instead of bfloat16 (HDN_TC_TAIL16; ~19 instead of ~16 significant bits)
   int pd_lo, ph_lo, pw_lo;    // patch origin = tile origin - p*_lo (padding in front of tap 0)
   int s2d;                    // 1: A operand is the space-to-depth view of a stride-2 convolution's input:
                               //    s2d pixel (d,h,w) holds channels (rd,rh,rw,c) = x[2d+rd][2h+rh][2w+rw][c], ldc == 4
@@ -177,12 +178,12 @@ __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 3, 128;"
 
 // Regroup the two channel quads a lane holds ([4*l8, +4) and [32 + 4*l8, +4)) with its neighbour lane into
 // 8-channel chunks and store the 16-byte chunk of pixel q.
-__device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q, bool qok, float4 v0, float4 v1, int lane) {
+__device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q, bool qok, float4 v0, float4 v1, int lane, bool v1_half = false) {
   const int l8 = lane & 7;
   const bool even = (l8 & 1) == 0;
   const int chunk = even ? (l8 >> 1) : (4 + (l8 >> 1));
   const uint32_t p00 = tc::pack_bf16x2(v0.x, v0.y), p01 = tc::pack_bf16x2(v0.z, v0.w);
-  const uint32_t p10 = tc::pack_bf16x2(v1.x, v1.y), p11 = tc::pack_bf16x2(v1.z, v1.w);
+  const uint32_t p10 = v1_half ? tc::pack_f16x2(v1.x, v1.y) : tc::pack_bf16x2(v1.x, v1.y), p11 = v1_half ? tc::pack_f16x2(v1.z, v1.w) : tc::pack_bf16x2(v1.z, v1.w);
   const uint32_t s0 = even ? p10 : p00, s1 = even ? p11 : p01;
   const uint32_t x0 = __shfl_xor_sync(0xffffffffu, s0, 1), x1 = __shfl_xor_sync(0xffffffffu, s1, 1);
   uint4 o;
@@ -394,12 +395,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const bool fast2 = p.fastx >= 2 && two && xmode1 == 1 && xmode >= 0;      // shapes xform_chunk2_any takes
           if (fast2) {
             const int j = warp & (nch - 1), c = j * 8;
-            tc::xform_chunk2_any(xmode, xmode1, p.split != 0, rawf0 + c, rawf1 + c, RS, vq0, vq1, p.P, (warp / nch) * 32 + lane,
+            tc::xform_chunk2_any(xmode, xmode1, p.split ? (p.tail16 ? 2 : 1) : 0, rawf0 + c, rawf1 + c, RS, vq0, vq1, p.P, (warp / nch) * 32 + lane,
                                  (8 / nch) * 32, ab0 + c, ab0 + p.CK + c, ab1 + c, ab1 + p.CK + c, c0 + c < p.K,
                                  dst + (uint32_t)j * (uint32_t)p.Ppad * 16u, dst + (uint32_t)(nch + j) * (uint32_t)p.Ppad * 16u);
           } else if (p.fastx && !two && xmode >= 0) {
             const int j = warp & (nch - 1), c = j * 8;          // this warp's chunk; 8 / nch warps share a chunk's pixels
-            tc::xform_chunk_any(xmode, p.split != 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
+            tc::xform_chunk_any(xmode, p.split ? (p.tail16 ? 2 : 1) : 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
                                 ab0 + c, ab0 + p.CK + c, c0 + c < p.K, dst + (uint32_t)j * (uint32_t)p.Ppad * 16u,
                                 dst + (uint32_t)(nch + j) * (uint32_t)p.Ppad * 16u);
           } else
@@ -450,8 +451,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 o.z = tc::pack_bf16x2(vb.x, vb.y); o.w = tc::pack_bf16x2(vb.z, vb.w);
               } else {                                             // head -> chunk j, tail -> chunk nch + j
                 uint4 t;
-                tc::pack_split_bf16x2(va.x, va.y, o.x, t.x); tc::pack_split_bf16x2(va.z, va.w, o.y, t.y);
-                tc::pack_split_bf16x2(vb.x, vb.y, o.z, t.z); tc::pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+                if (p.tail16) {
+                  tc::pack_split_bf16_f16x2(va.x, va.y, o.x, t.x); tc::pack_split_bf16_f16x2(va.z, va.w, o.y, t.y);
+                  tc::pack_split_bf16_f16x2(vb.x, vb.y, o.z, t.z); tc::pack_split_bf16_f16x2(vb.z, vb.w, o.w, t.w);
+                } else {
+                  tc::pack_split_bf16x2(va.x, va.y, o.x, t.x); tc::pack_split_bf16x2(va.z, va.w, o.y, t.y);
+                  tc::pack_split_bf16x2(vb.x, vb.y, o.z, t.z); tc::pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+                }
                 if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)(nch + j) * (uint32_t)p.Ppad * 16u) = t;
               }
               if (qok) *reinterpret_cast<uint4*>(drow + (uint32_t)j * (uint32_t)p.Ppad * 16u) = o;
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               r1.x = x.x - __bfloat162float(__float2bfloat16_rn(x.x)); r1.y = x.y - __bfloat162float(__float2bfloat16_rn(x.y));
               r1.z = x.z - __bfloat162float(__float2bfloat16_rn(x.z)); r1.w = x.w - __bfloat162float(__float2bfloat16_rn(x.w));
             }
-            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, r0[u], r1, lane);
+            store_chunks(dst, (uint32_t)p.Ppad, q, q < p.P, r0[u], r1, lane, p.split && p.tail16);
           }
         }
         tc::fence_proxy_async_smem();
@@ -541,6 +547,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // =================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 0, 0);
+      // bf16x3 cross terms: the tail operand is bfloat16 (format 1) or IEEE half (format 0, HDN_TC_TAIL16)
+      const uint32_t idesc_lh = tc::make_idesc_f16kind(128, p.BN, p.tail16 ? 0 : 1, 1, 0, 0);    // A tail x B head
+      const uint32_t idesc_hl = tc::make_idesc_f16kind(128, p.BN, 1, p.tail16 ? 0 : 1, 0, 0);    // A head x B tail
       const uint32_t lbo_a = (uint32_t)p.Ppad * 16u, sbo_a = (uint32_t)p.PW * 16u;
       const uint32_t lbo_b = (uint32_t)p.BN * 16u, sbo_b = 128u;
       StageIt it;
@@ -601,8 +610,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             // bf16x3: tails first (small terms), head x head last; tail operands sit CK/8 chunks behind the heads
             for (int s = 0; s < nk; ++s) {
               const uint64_t ah = ad + (uint64_t)s * kstep_a, bh = bd + (uint64_t)s * kstep_b;
-              tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc, acc);
-              tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc, 1u);
+              tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc_lh, acc);
+              tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc_hl, 1u);
               tc::umma_bf16(tmem_d, ah, bh, idesc, 1u);
               acc = 1;
             }
@@ -894,7 +903,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 //   role 1 (dgrad): B[n][k] = w[flip(tap)][n][k]                 K = Cout, NC = Cin
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                            int Cin, int Cout, int kd, int kh, int kw, int BN, int KB,
-                                                           int KC, int role, int nsplit, int fold, long long total16) {
+                                                           int KC, int role, int nsplit, int fold, int tail16, long long total16) {
   // one thread per 16-byte output unit (n, chunk j): 8 consecutive k.  role 0 reads w[tap][k][col] (threads
   // adjacent in n -> coalesced over col); role 1 reads w[tap'][col][k..k+8) (two float4 per thread).
   const int T = kd * kh * kw;
@@ -928,8 +937,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
       for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16_rn(v[e]));
     }
     uint4 o;
-    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
-    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    if (part && tail16) {
+      o.x = tc::pack_f16x2(v[0], v[1]); o.y = tc::pack_f16x2(v[2], v[3]);
+      o.z = tc::pack_f16x2(v[4], v[5]); o.w = tc::pack_f16x2(v[6], v[7]);
+    } else {
+      o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
+      o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    }
     reinterpret_cast<uint4*>(out)[idx] = o;
   }
 }
@@ -940,7 +954,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 //   role 1 (dgrad): B[n = (rd,rh,rw,c)][k = co] = w[t(3 - tq', r)][c][co]   (taps flipped)
 __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                                                int Cin, int Cout, int three_d, int BN, int KB, int KC,
-                                                               int role, int nsplit, int fold, long long total16) {
+                                                               int role, int nsplit, int fold, int tail16, long long total16) {
   const int TD = three_d ? 4 : 1, T = TD * 16;
   const int quads = three_d ? 8 : 4;
   const int K = role == 0 ? quads * 4 : Cout, NC = role == 0 ? Cout : quads * 4;
@@ -972,8 +986,13 @@ __global__ void __launch_bounds__(256) pack_weights_s2d_kernel(const float* __re
       if (part) v[e] -= __bfloat162float(__float2bfloat16_rn(v[e]));
     }
     uint4 o;
-    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
-    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    if (part && tail16) {
+      o.x = tc::pack_f16x2(v[0], v[1]); o.y = tc::pack_f16x2(v[2], v[3]);
+      o.z = tc::pack_f16x2(v[4], v[5]); o.w = tc::pack_f16x2(v[6], v[7]);
+    } else {
+      o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
+      o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    }
     reinterpret_cast<uint4*>(out)[idx] = o;
   }
 }
@@ -1010,6 +1029,17 @@ int hdn_tc_x3fold() {
   }
   return v;
 }
+
+// HDN_TC_TAIL16=0|1: tails of the bf16x3 operands as IEEE half (1) instead of bfloat16 (0); also hdn_set_switch()
+static int g_tail16 = -1;
+int hdn_tc_tail16() {
+  if (g_tail16 < 0) {
+    const char* e = getenv("HDN_TC_TAIL16");
+    g_tail16 = e ? (atoi(e) != 0 ? 1 : 0) : 0;
+  }
+  return g_tail16;
+}
+void hdn_tc_tail16_set(int v) { g_tail16 = v ? 1 : 0; }
 
 // HDN_TC_L2PF=1: experiment switch, see TcParams::l2pf (default 0)
 int hdn_tc_l2pf() {
@@ -1172,13 +1202,14 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     attr_set = true;
   }
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(c->ws);
+  const int tail16 = (nsplit == 2 && !pl.fold && hdn_tc_tail16()) ? 1 : 0;
   {
     long long total = pl.ws_elems / 8;
     unsigned gr = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     if (g.s2d || g.scatter)
-      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, total);
+      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
     else
-      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, total);
+      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
     HDN_CHECK_LAUNCH("pack_weights");
   }
   TcParams p;
@@ -1200,6 +1231,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.wpack = wp;
   p.mode = mode;
   p.split = nsplit == 2 ? 1 : 0;
+  p.tail16 = tail16;
   p.fastx = hdn_tc_fastx();
   p.l2pf = hdn_tc_l2pf();
   p.fold = pl.fold;

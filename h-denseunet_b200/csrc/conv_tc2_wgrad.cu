@@ -46,6 +46,7 @@ struct Wg2Params {
   int Cin, Cout;
   int BN, G, groups, ci_tiles, co_tiles;
   int flat, layout, order;
+  int debug;                          // timing experiments (HDN_TC2_DEBUG, results invalid): 1 = no TMA traffic, 2 = K-major operand bits, 4 = N forced to 64
   int PH, PW;
   int unitA, boxA, nunitA_max;        // stride / TMA box bytes of one A unit (plane or 64-channel block); units per stage
   int cwA;                            // channels per A unit
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
         int n_img, d0, h0, w0;
         long long m0;
         if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
+        if (p.debug & 1) break;                           // timing experiment: the MMA stream alone
         tc::mbar_wait(&empty[st], ph ^ 1);
         tc::mbar_arrive_expect_tx(&full[st], tx_bytes);
         uint8_t* sA = smem + (size_t)st * p.stage_bytes;
@@ -161,7 +163,8 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
   } else if (warp == 1) {
     // =================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 1, 1);
+      const uint32_t idesc = (p.debug & 2) ? tc::make_idesc_bf16(128, (p.debug & 4) ? 64 : p.BN, 0, 0)
+                                           : tc::make_idesc_bf16(128, (p.debug & 4) ? 64 : p.BN, 1, 1);
       // A: K group (8 pixels) stride = one patch row; MN group stride = one unit (plane / 64-channel block)
       const uint32_t pix = p.layout ? 128u : 16u;                      // bytes per patch pixel inside a unit
       const uint64_t adesc_hi = p.layout ? make_smem_desc_sw128(0, (uint32_t)p.unitA, (uint32_t)p.PW * pix)
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
         int n_img, d0, h0, w0;
         long long m0;
         if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
-        tc::mbar_wait(&full[st], ph);
+        if (!(p.debug & 1)) tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
         const uint8_t* sA = smem + (size_t)st * p.stage_bytes;
         const uint64_t ad0 = adesc_hi | (uint64_t)((tc::smem_u32(sA) >> 4) & 0x3FFF);
@@ -523,7 +526,8 @@ int hdn_conv_wgrad_tc2(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.Cin = c->Cin; p.Cout = c->Cout;
   p.BN = pl.BN; p.G = pl.G; p.groups = pl.groups; p.ci_tiles = pl.ci_tiles; p.co_tiles = pl.co_tiles;
   p.flat = pl.flat; p.layout = pl.layout; p.PH = pl.PH; p.PW = pl.PW;
-  { const char* e = getenv("HDN_TC2_ORDER"); p.order = e ? atoi(e) : 1; }
+  { const char* e = getenv("HDN_TC2_ORDER"); p.order = e ? atoi(e) : 0; }       // 0 = tap-major (measured faster on B200, profiles/r02c_*)
+  { const char* e = getenv("HDN_TC2_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.unitA = pl.unitA; p.boxA = pl.boxA; p.nunitA_max = pl.nunitA_max; p.cwA = pl.cwA;
   p.stage_bytes = pl.stage_bytes; p.offB = pl.offB; p.NS = pl.NS;
   p.pd_lo = c->kd / 2; p.ph_lo = c->kh / 2; p.pw_lo = c->kw / 2;

@@ -372,13 +372,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           const int xmode1 = !two ? -1 : ((pa1 && pb1 && relu1 != 0) ? 1 : ((!pa1 && !pb1 && relu1 == 0) ? 0 : -1));
           if (p.fastx >= 2 && two && xmode1 == 1 && xmode >= 0) {
             const int nch = CW >> 3, j = warp & (nch - 1), c = j * 8;
-            tc::xform_chunk2_any(xmode, xmode1, p.split != 0, rawf0 + c, rawf1 + c, RS, vq0, vq1, p.P, (warp / nch) * 32 + lane,
+            tc::xform_chunk2_any(xmode, xmode1, p.split != 0 ? 1 : 0, rawf0 + c, rawf1 + c, RS, vq0, vq1, p.P, (warp / nch) * 32 + lane,
                                  (8 / nch) * 32, ab0 + c, ab0 + CW + c, ab1 + c, ab1 + CW + c, c0 + c < p.Cin,
                                  dst + (uint32_t)j * (uint32_t)p.Ppad * 16u, dst + a_tail + (uint32_t)j * (uint32_t)p.Ppad * 16u);
           } else if (p.fastx && !two && xmode >= 0) {
             // warp-per-chunk form (tc::xform_chunk): the chunk's (a, b) stay in registers for the whole sub-stage
             const int nch = CW >> 3, j = warp & (nch - 1), c = j * 8;
-            tc::xform_chunk_any(xmode, p.split != 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
+            tc::xform_chunk_any(xmode, p.split != 0 ? 1 : 0, rawf0 + c, RS, vq0, p.P, (warp / nch) * 32 + lane, (8 / nch) * 32,
                                 ab0 + c, ab0 + CW + c, c0 + c < p.Cin, dst + (uint32_t)j * (uint32_t)p.Ppad * 16u,
                                 dst + a_tail + (uint32_t)j * (uint32_t)p.Ppad * 16u);
           } else

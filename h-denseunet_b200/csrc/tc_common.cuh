@@ -4,6 +4,7 @@
 // descriptor" tables for tcgen05 (kind::f16, SWIZZLE_NONE canonical layouts).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc {
@@ -95,6 +96,18 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a
   d |= (uint32_t)(M >> 4) << 24;
   return d;
 }
+// Same, with the operand formats spelled out: 0 = F16, 1 = BF16 (kind::f16 takes either for A and for B).
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16kind(int M, int N, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                         // c_format = F32
+  d |= (uint32_t)(a_fmt & 7) << 7;
+  d |= (uint32_t)(b_fmt & 7) << 10;
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
 // D[tmem] (+)= A[smem] * B[smem];  one thread issues on behalf of the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -140,15 +153,32 @@ __device__ __forceinline__ void pack_split_bf16x2(float a, float b, uint32_t& he
   head = *reinterpret_cast<const uint32_t*>(&h);
   tail = pack_bf16x2(a - hf.x, b - hf.y);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// same split with the tail kept in IEEE half precision: the residual x - head is <= 2^-9 |x|, and a half carries 11
+// significant bits of it against bfloat16's 8, so head + tail carries ~19 significant bits instead of ~16 (the MMA pairs a
+// bf16 operand with an f16 one: kind::f16 takes the two formats independently for A and B)
+__device__ __forceinline__ void pack_split_bf16_f16x2(float a, float b, uint32_t& head, uint32_t& tail) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float2 hf = __bfloat1622float2(h);
+  head = *reinterpret_cast<const uint32_t*>(&h);
+  tail = pack_f16x2(a - hf.x, b - hf.y);
+}
+template <int SPLIT>
+__device__ __forceinline__ void pack_split_any(float a, float b, uint32_t& head, uint32_t& tail) {
+  if (SPLIT == 2) pack_split_bf16_f16x2(a, b, head, tail); else pack_split_bf16x2(a, b, head, tail);
+}
 
 // Operand transform, warp-per-chunk form: one warp turns ONE 8-channel chunk of a raw fp32 stage (pixel stride RS
 // floats) into bf16 for the pixels q0, q0 + qstep, ... (lane = pixel).  The chunk's per-channel (a, b) are read once and
 // stay in registers for the whole stage, and the prologue form is a compile-time constant, so a pixel costs two 16-byte
 // reads, 8 FFMA + 8 FMNMX (MODE 1), 4 packs and one 16-byte store.
 //   MODE 0: y = x            MODE 1: y = max(a*x + b, 0)   (BatchNorm -> Scale -> ReLU folded; hdn_src.pa/pb/relu all set)
-//   SPLIT : also store the bf16 tail (x - head) at dtail (bf16x3)
+//   SPLIT : 1 / 2: also store the tail (x - head) at dtail (bf16x3), as bfloat16 (1) or as IEEE half (2)
 // vq[q] = source-patch pixel of virtual pixel q, or -1 => zero padding (applied after the prologue, like ZeroPadding).
-template <int MODE, bool SPLIT>
+template <int MODE, int SPLIT>
 __device__ __forceinline__ void xform_px(float4 va, float4 vb, const float4& a0, const float4& a1, const float4& b0,
                                          const float4& b1, bool ok, uint4& o, uint4& t) {
   if (MODE == 1) {
@@ -158,8 +188,8 @@ __device__ __forceinline__ void xform_px(float4 va, float4 vb, const float4& a0,
     vb.z = fmaxf(fmaf(a1.z, vb.z, b1.z), 0.f); vb.w = fmaxf(fmaf(a1.w, vb.w, b1.w), 0.f);
   }
   if (SPLIT) {
-    pack_split_bf16x2(va.x, va.y, o.x, t.x); pack_split_bf16x2(va.z, va.w, o.y, t.y);
-    pack_split_bf16x2(vb.x, vb.y, o.z, t.z); pack_split_bf16x2(vb.z, vb.w, o.w, t.w);
+    pack_split_any<SPLIT>(va.x, va.y, o.x, t.x); pack_split_any<SPLIT>(va.z, va.w, o.y, t.y);
+    pack_split_any<SPLIT>(vb.x, vb.y, o.z, t.z); pack_split_any<SPLIT>(vb.z, vb.w, o.w, t.w);
     if (!ok) t = make_uint4(0u, 0u, 0u, 0u);
   } else {
     o.x = pack_bf16x2(va.x, va.y); o.y = pack_bf16x2(va.z, va.w);
@@ -167,7 +197,7 @@ __device__ __forceinline__ void xform_px(float4 va, float4 vb, const float4& a0,
   }
   if (!ok) o = make_uint4(0u, 0u, 0u, 0u);                // zero padding / channels past K: applied after the prologue
 }
-template <int MODE, bool SPLIT>
+template <int MODE, int SPLIT>
 __device__ __forceinline__ void xform_chunk(const float* rawc, int RS, const int* vq, int P, int q0, int qstep,
                                             const float* a8, const float* b8, bool cvalid, uint8_t* dchunk, uint8_t* dtail) {
   float4 a0 = make_float4(1.f, 1.f, 1.f, 1.f), a1 = a0, b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
@@ -209,7 +239,7 @@ __device__ __forceinline__ void xform_apply(float4& va, float4& vb, const float4
     vb.z = fmaxf(fmaf(a1.z, vb.z, b1.z), 0.f); vb.w = fmaxf(fmaf(a1.w, vb.w, b1.w), 0.f);
   }
 }
-template <int M0, int M1, bool SPLIT>
+template <int M0, int M1, int SPLIT>
 __device__ __forceinline__ void xform_chunk2(const float* raw0c, const float* raw1c, int RS, const int* vq0, const int* vq1,
                                              int P, int q0, int qstep, const float* a80, const float* b80, const float* a81,
                                              const float* b81, bool cvalid, uint8_t* dchunk, uint8_t* dtail) {
@@ -241,33 +271,37 @@ __device__ __forceinline__ void xform_chunk2(const float* raw0c, const float* ra
 }
 // the two-source shapes the networks contain: (BN+ReLU, BN+ReLU) = fianl_conv (hybridnet.py:414-415) and
 // (plain, BN+ReLU) = the skip-add decoder (denseunet.py:190-209).  Returns false for any other combination.
-__device__ __forceinline__ bool xform_chunk2_any(int m0, int m1, bool split, const float* raw0c, const float* raw1c, int RS,
+__device__ __forceinline__ bool xform_chunk2_any(int m0, int m1, int split, const float* raw0c, const float* raw1c, int RS,
                                                  const int* vq0, const int* vq1, int P, int q0, int qstep, const float* a80,
                                                  const float* b80, const float* a81, const float* b81, bool cvalid,
                                                  uint8_t* dchunk, uint8_t* dtail) {
   if (m0 == 1 && m1 == 1) {
-    if (split) xform_chunk2<1, 1, true>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
-    else       xform_chunk2<1, 1, false>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    if (split == 2)  xform_chunk2<1, 1, 2>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    else if (split)  xform_chunk2<1, 1, 1>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    else             xform_chunk2<1, 1, 0>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
     return true;
   }
   if (m0 == 0 && m1 == 1) {
-    if (split) xform_chunk2<0, 1, true>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
-    else       xform_chunk2<0, 1, false>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    if (split == 2)  xform_chunk2<0, 1, 2>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    else if (split)  xform_chunk2<0, 1, 1>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
+    else             xform_chunk2<0, 1, 0>(raw0c, raw1c, RS, vq0, vq1, P, q0, qstep, a80, b80, a81, b81, cvalid, dchunk, dtail);
     return true;
   }
   return false;
 }
 
 // dispatch on the two runtime-uniform switches
-__device__ __forceinline__ void xform_chunk_any(int mode, bool split, const float* rawc, int RS, const int* vq, int P, int q0,
+__device__ __forceinline__ void xform_chunk_any(int mode, int split, const float* rawc, int RS, const int* vq, int P, int q0,
                                                 int qstep, const float* a8, const float* b8, bool cvalid, uint8_t* dchunk,
                                                 uint8_t* dtail) {
   if (mode == 1) {
-    if (split) xform_chunk<1, true>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
-    else       xform_chunk<1, false>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    if (split == 2)  xform_chunk<1, 2>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    else if (split)  xform_chunk<1, 1>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    else             xform_chunk<1, 0>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
   } else {
-    if (split) xform_chunk<0, true>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
-    else       xform_chunk<0, false>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    if (split == 2)  xform_chunk<0, 2>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    else if (split)  xform_chunk<0, 1>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
+    else             xform_chunk<0, 0>(rawc, RS, vq, P, q0, qstep, a8, b8, cvalid, dchunk, dtail);
   }
 }
 

@@ -228,6 +228,22 @@ int hdn_window_accumulate(const float* logits, float* score, int* count, int S, 
                           int z0, void* stream);
 int hdn_window_finalize(float* score, const int* count, int Z, int64_t HW, void* stream);
 
+/* Post-processing of the probability volumes (test.py:71-115, lib/funcs.py:138-153), volumes in the reference's C-order
+ * (X, Y, Z) layout, one uint8 per voxel; ws >= 8 * X*Y*Z + 8 bytes of device scratch (labels + sizes / flags).
+ *   threshold : liver = (s_liver >= t_liver) | tumor, tumor = s_tumor >= t_tumor            (test.py:73-77)
+ *   dilate    : ndimage.binary_dilation, 6-neighbour structure, one iteration               (test.py:62,95)
+ *   largest_component : measure.label (26-connectivity) + regionprops area + box.index(max) (test.py:83-91,96-103)
+ *   fill_holes: ndimage.binary_fill_holes (6-connected background not reaching the border)  (test.py:104,109,112)
+ *   and / compose: Segmask * liver_labels; liver_res[Segmask == 1] = 2                      (test.py:108,113) */
+int hdn_post_threshold(const float* score_liver, const float* score_tumor, unsigned char* liver, unsigned char* tumor,
+                       int64_t n, float thres_liver, float thres_tumor, void* stream);
+int hdn_post_dilate(const unsigned char* in, unsigned char* out, int X, int Y, int Z, void* stream);
+int hdn_post_largest_component(const unsigned char* in, unsigned char* out, int X, int Y, int Z, void* ws, int64_t ws_bytes,
+                               void* stream);
+int hdn_post_fill_holes(const unsigned char* in, unsigned char* out, int X, int Y, int Z, void* ws, int64_t ws_bytes, void* stream);
+int hdn_post_and(const unsigned char* a, const unsigned char* b, unsigned char* out, int64_t n, void* stream);
+int hdn_post_compose(const unsigned char* liver, const unsigned char* tumor, unsigned char* out, int64_t n, void* stream);
+
 /* Raw device memory + CUDA IPC for the parameter / gradient arenas that the per-GPU
  * processes map into each other (handle = 64 bytes, cudaIpcMemHandle_t). */
 int hdn_dev_malloc(void** out, int64_t bytes);

@@ -215,7 +215,9 @@ def test_sliding_window_mixed_and_slice_reuse(cuda_dev):
     assert rel_l2(s1, o1) < 1e-3
     # 2-D slice reuse: the same kernels on the same inputs -> bit-identical volumes, about half the 2-D evaluations
     r1, r2 = hdn.predict_tumor_inwindow(m, vol, 3, mini, maxi, a, reuse_2d=True, stats=st1)
-    assert np.array_equal(s1, r1) and np.array_equal(s2, r2)
+    d1, d2 = float(np.abs(s1 - r1).max()), float(np.abs(s2 - r2).max())
+    print("slice reuse: max |diff| %.3e %.3e, 2-D slice evaluations %d -> %d" % (d1, d2, st0["slices_2d"], st1["slices_2d"]))
+    assert d1 == 0.0 and d2 == 0.0, (d1, d2)
     assert st1["slices_2d"] <= 0.6 * st0["slices_2d"]
 
 

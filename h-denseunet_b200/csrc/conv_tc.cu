@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 8) {
     // =================================================================== weight loader (TMA engine)
-    if (lane == 0) {
+    // all 32 lanes run the loop converged; one elected lane issues (see tc::elect_one_sync)
+    {
       StageIt it;
       it_init(p, it);
       int sb = 0;
@@ -536,8 +537,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const __nv_bfloat16* src = p.wpack + (((size_t)it.t.n_tile * p.KB + it.kb) * T + (size_t)it.dz * taps_hw) * blk;
         for (int t2 = 0; t2 < taps_hw; ++t2, src += blk) {
           tc::mbar_wait(&b_empty[sb], phb ^ 1);
-          tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
-          tc::bulk_g2s(sB + sb * B_BYTES, src, B_BYTES, &b_full[sb]);
+          if (tc::elect_one_sync()) {
+            tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+            tc::bulk_g2s(sB + sb * B_BYTES, src, B_BYTES, &b_full[sb]);
+          }
+          __syncwarp();
           if (++sb == p.nsb) { sb = 0; phb ^= 1; }
         }
         it_next(p, it);
@@ -545,7 +549,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 9) {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    // all 32 lanes run the loop converged (waits, iterators); the tcgen05.mma / commit issue sits under elect_one_sync
+    {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.BN, 0, 0);
       // bf16x3 cross terms: the tail operand is bfloat16 (format 1) or IEEE half (format 0, HDN_TC_TAIL16)
       const uint32_t idesc_lh = tc::make_idesc_f16kind(128, p.BN, p.tail16 ? 0 : 1, 1, 0, 0);    // A tail x B head
@@ -593,6 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           TT_ADD(t_bfull);
           const uint64_t ad = a_desc0 + tap_units;
           const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
+          if (tc::elect_one_sync()) {
           if (!p.split) {
             tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
             if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
@@ -613,27 +619,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc_lh, acc);
               tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc_hl, 1u);
               tc::umma_bf16(tmem_d, ah, bh, idesc, 1u);
-              acc = 1;
+              acc = 1;                                   // (elected lane's copy; every lane sets it after the tap)
             }
           }
-          acc = 1;
           tc::umma_commit(&b_empty[sb]);
+          }
+          __syncwarp();
+          acc = 1;
           if (++sb == p.nsb) { sb = 0; phb ^= 1; }
           if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;
           TT_ADD(t_mma);
         }
-        tc::umma_commit(&a_empty[sa]);
-        if (++sa == NSA) { sa = 0; pha ^= 1; }
         const int seq_before = it.seq;
+        const int sa_done = sa;
+        if (++sa == NSA) { sa = 0; pha ^= 1; }
         it_next(p, it);
-        if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
+        if (tc::elect_one_sync()) {
+          tc::umma_commit(&a_empty[sa_done]);
+          if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
+        }
+        __syncwarp();
         TT_ADD(t_mma);
 #ifdef HDN_TC_TIMING
         ++n_st;
 #endif
       }
 #ifdef HDN_TC_TIMING
-      if (blockIdx.x == 0)
+      if (blockIdx.x == 0 && lane == 0)
         printf("[mma] stages %lld  acc_empty %lld  a_full %lld  b_full %lld  issue %lld (cycles/stage)\n", n_st, t_acc / n_st, t_afull / n_st,
                t_bfull / n_st, t_mma / n_st);
 #endif
@@ -1030,16 +1042,11 @@ int hdn_tc_x3fold() {
   return v;
 }
 
-// HDN_TC_TAIL16=0|1: tails of the bf16x3 operands as IEEE half (1) instead of bfloat16 (0); also hdn_set_switch()
-static int g_tail16 = -1;
-int hdn_tc_tail16() {
-  if (g_tail16 < 0) {
-    const char* e = getenv("HDN_TC_TAIL16");
-    g_tail16 = e ? (atoi(e) != 0 ? 1 : 0) : 0;
-  }
-  return g_tail16;
-}
-void hdn_tc_tail16_set(int v) { g_tail16 = v ? 1 : 0; }
+// Tails of the bf16x3 operands as IEEE half instead of bfloat16 (3 more significant bits per operand) would need MMAs
+// that pair a bf16 operand with an f16 one.  The instruction descriptor has separate A / B format fields, but sm_100a
+// rejects the mix: the kernel dies with "an illegal instruction was encountered" (B200, round 2, gpurun_out/r2d_*).
+// The code path is kept behind this constant for the record; it is never enabled.
+int hdn_tc_tail16() { return 0; }
 
 // HDN_TC_L2PF=1: experiment switch, see TcParams::l2pf (default 0)
 int hdn_tc_l2pf() {

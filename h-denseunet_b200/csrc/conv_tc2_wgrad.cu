@@ -134,10 +134,9 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
   const uint32_t tx_bytes = (uint32_t)nuA * (uint32_t)p.boxA + (uint32_t)nuB * 2048u;        // bytes the copy engine reports per stage
 
   if (warp == 0) {
-    // =================================================================== TMA producer
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmA);
-      tma_prefetch_desc(&p.tmB);
+    // =================================================================== TMA producer (all lanes converged, one elected lane issues)
+    {
+      if (tc::elect_one_sync()) { tma_prefetch_desc(&p.tmA); tma_prefetch_desc(&p.tmB); }
       int st = 0;
       uint32_t ph = 0;
       for (long long t = split; t < p.n_pos_tiles; t += nsplit) {
@@ -146,23 +145,26 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
         if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
         if (p.debug & 1) break;                           // timing experiment: the MMA stream alone
         tc::mbar_wait(&empty[st], ph ^ 1);
-        tc::mbar_arrive_expect_tx(&full[st], tx_bytes);
-        uint8_t* sA = smem + (size_t)st * p.stage_bytes;
-        uint8_t* sB = sA + p.offB;
-        if (p.flat) {
-          for (int u = 0; u < nuA; ++u) tma_load_2d(sA + (size_t)u * p.unitA, &p.tmA, &full[st], ci0 + u * p.cwA, (int)m0);
-          for (int u = 0; u < nuB; ++u) tma_load_2d(sB + (size_t)u * 2048, &p.tmB, &full[st], co0 + u * 8, (int)m0);
-        } else {
-          const int aw = w0 - p.pw_lo + gtw0, ah = h0 - p.ph_lo + gth0, ad = d0 - p.pd_lo + gdz;
-          for (int u = 0; u < nuA; ++u) tma_load_5d(sA + (size_t)u * p.unitA, &p.tmA, &full[st], ci0 + u * p.cwA, aw, ah, ad, n_img);
-          for (int u = 0; u < nuB; ++u) tma_load_5d(sB + (size_t)u * 2048, &p.tmB, &full[st], co0 + u * 8, w0, h0, d0, n_img);
+        if (tc::elect_one_sync()) {
+          tc::mbar_arrive_expect_tx(&full[st], tx_bytes);
+          uint8_t* sA = smem + (size_t)st * p.stage_bytes;
+          uint8_t* sB = sA + p.offB;
+          if (p.flat) {
+            for (int u = 0; u < nuA; ++u) tma_load_2d(sA + (size_t)u * p.unitA, &p.tmA, &full[st], ci0 + u * p.cwA, (int)m0);
+            for (int u = 0; u < nuB; ++u) tma_load_2d(sB + (size_t)u * 2048, &p.tmB, &full[st], co0 + u * 8, (int)m0);
+          } else {
+            const int aw = w0 - p.pw_lo + gtw0, ah = h0 - p.ph_lo + gth0, ad = d0 - p.pd_lo + gdz;
+            for (int u = 0; u < nuA; ++u) tma_load_5d(sA + (size_t)u * p.unitA, &p.tmA, &full[st], ci0 + u * p.cwA, aw, ah, ad, n_img);
+            for (int u = 0; u < nuB; ++u) tma_load_5d(sB + (size_t)u * 2048, &p.tmB, &full[st], co0 + u * 8, w0, h0, d0, n_img);
+          }
         }
+        __syncwarp();
         if (++st == p.NS) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // =================================================================== MMA issuer
-    if (lane == 0) {
+    // =================================================================== MMA issuer (all lanes converged, one elected lane issues)
+    {
       const uint32_t idesc = (p.debug & 2) ? tc::make_idesc_bf16(128, (p.debug & 4) ? 64 : p.BN, 0, 0)
                                            : tc::make_idesc_bf16(128, (p.debug & 4) ? 64 : p.BN, 1, 1);
       // A: K group (8 pixels) stride = one patch row; MN group stride = one unit (plane / 64-channel block)
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
         if (!tile_valid(t, n_img, d0, h0, w0, m0)) continue;
         if (!(p.debug & 1)) tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
+        if (tc::elect_one_sync()) {
         const uint8_t* sA = smem + (size_t)st * p.stage_bytes;
         const uint64_t ad0 = adesc_hi | (uint64_t)((tc::smem_u32(sA) >> 4) & 0x3FFF);
         const uint64_t bd0 = bdesc_hi | (uint64_t)((tc::smem_u32(sA + p.offB) >> 4) & 0x3FFF);
@@ -213,11 +216,14 @@ __global__ void __launch_bounds__(W2_THREADS, 1) conv_wgrad_tc2_kernel(const __g
             }
           }
         }
-        acc = 1;
         tc::umma_commit(&empty[st]);
+        }
+        __syncwarp();
+        acc = 1;
         if (++st == p.NS) { st = 0; ph ^= 1; }
       }
-      tc::umma_commit(acc_full);
+      if (tc::elect_one_sync()) tc::umma_commit(acc_full);
+      __syncwarp();
     }
   } else {
     // =================================================================== epilogue: TMEM -> dW (vector reductions)

@@ -616,7 +616,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
     }
   } else {
     // =================================================================== MMA issuer
-    if (lane == 0) {
+    // all 32 lanes run the loop converged; the tcgen05.mma / commit issue sits under tc::elect_one_sync
+    {
       const uint32_t idesc = tc::make_idesc_bf16(128, p.BNe, 1, 1);
       const uint32_t a_lbo = (uint32_t)p.PW * 16u, a_sbo = (uint32_t)p.Ppad * 16u;   // K-group / MN-group strides
       const uint32_t b_lbo = 128u, b_sbo = 129u * 16u;
@@ -637,7 +638,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
         tc::mbar_wait(&full[st], ph);
         tc::tc_fence_after();
         WT_ADD(t_full);
-        // lean issue loop (one serial thread): descriptors are advanced by integer adds on the 14-bit start-address field
+        if (tc::elect_one_sync()) {
+        // lean issue loop (one elected lane): descriptors are advanced by integer adds on the 14-bit start-address field
         const uint64_t ad0 = adesc_hi | (uint64_t)((tc::smem_u32(sA + st * A_BYTES) >> 4) & 0x3FFF);
         const uint64_t bd0 = bdesc_hi | (uint64_t)((tc::smem_u32(sB + st * B_BYTES) >> 4) & 0x3FFF);
         uint32_t tap_units = tap_units0;                     // ((th - gth0) * PW + (tw - gtw0)) in 16-byte units
@@ -650,17 +652,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_wgrad_tc_kernel(const __gr
           for (int r = 1; r < 8; ++r) tc::umma_bf16(tm, ad + (uint64_t)(r * row2), bd0 + (uint64_t)(r * 16), idesc, 1u);
           if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;
         }
-        acc = 1;
         tc::umma_commit(&empty[st]);
+        }
+        __syncwarp();
+        acc = 1;
         if (++st == NS) { st = 0; ph ^= 1; }
         WT_ADD(t_mma);
 #ifdef HDN_TC_TIMING
         ++n_tile;
 #endif
       }
-      tc::umma_commit(acc_full);
+      if (tc::elect_one_sync()) tc::umma_commit(acc_full);
+      __syncwarp();
 #ifdef HDN_TC_TIMING
-      if (blockIdx.x == 0 && blockIdx.y == 0 && n_tile > 0)
+      if (blockIdx.x == 0 && blockIdx.y == 0 && n_tile > 0 && lane == 0)
         printf("[wgrad mma] tiles %lld  full_wait %lld  issue %lld (cycles/tile)  G %d BNe %d\n", n_tile, t_full / n_tile, t_mma / n_tile, p.G, p.BNe);
 #endif
     }

@@ -46,6 +46,23 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
+// One lane of a CONVERGED warp.  Single-thread roles (tcgen05.mma issue, TMA issue) run their loops with all 32 lanes
+// converged and put only the issue itself under this predicate: ptxas then emits the uniform-datapath instruction
+// (UTCHMMA / UTMALDG) once, straight-line.  Under `if (lane == 0)` the region is divergent for the compiler and every
+// such instruction is wrapped in its own ELECT / BRA.U.ANY serialisation loop with R2UR moves in front of it
+// (~9 instructions and ~50 issue cycles per MMA: measured, profiles/r02d_tc2_mma_issue.txt).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %2;\n\t"
+      "@px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -269,29 +269,3 @@ def test_wgrad_tc2_vs_fp32_and_gen1(cuda_dev, name, layout):
     assert rel_l2(w2, w1) < 1e-4, (name, rel_l2(w2, w1))
     if b0 is not None:
         assert rel_l2(b2, b0) < 1e-4
-
-
-# ---- bf16x3 with IEEE-half tails (HDN_TC_TAIL16): head bf16 + tail f16 carries ~19 significant bits ------------------
-@pytest.mark.parametrize("name", ["1x1_flat", "3x3_dense", "3x3x3_dense", "3x3x3_up222_bias_stats", "3x3x3_two_src", "stem3d_7x7x7s2",
-                                  "3x3_up_skip_bias_stats"])
-def test_x3_half_tails_fprop_dgrad(cuda_dev, name):
-    """The two cross-term MMAs pair a bf16 operand with an f16 one (kind::f16 takes the formats per operand): the result
-    must be correct (a format mix-up gives O(1e-2)) and closer to the fp32 FMA kernel than the all-bf16 split."""
-    kw = dict(CASES[name])
-    kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
-    errs = {}
-    stem = name.startswith("stem")
-    try:
-        for t16 in (0, 1):
-            _switch("HDN_TC_TAIL16", t16)
-            c = Case(cuda_dev, tc=2, **kw)
-            y0, _, _ = c.fprop(0)
-            y1, _, _ = c.fprop(2)
-            r0 = c.dgrad(0, 0, False, with_sums=not stem)
-            r1 = c.dgrad(2, 0, False, with_sums=not stem)
-            errs[t16] = (rel_l2(y1, y0), max(rel_l2(g1, g0) for (g0, _), (g1, _) in zip(r0, r1)))
-    finally:
-        _switch("HDN_TC_TAIL16", 0)
-    print("x3 tails %s: bf16 fprop %.2e dgrad %.2e | f16 fprop %.2e dgrad %.2e" % ((name,) + errs[0] + errs[1]))
-    assert errs[1][0] < 2e-5 and errs[1][1] < 2e-5, errs
-    assert errs[1][0] < 0.6 * errs[0][0] and errs[1][1] < 0.6 * errs[0][1], errs

@@ -56,7 +56,7 @@ constexpr int NSB_MAX = 16;   // weight-block ring depth upper bound
 constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs at most 3 stages ahead of the transform)
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
-constexpr int RB = 32;        // dgrad epilogue: rows fetched ahead per lane
+constexpr int RB = 16;        // dgrad epilogue, scalar fallback form: rows fetched ahead per lane
 constexpr int MAXC0 = 14;     // copies per producer thread and stage, source 0 (4-tap stems' dgrad: 19x11 px x 16 quads / 256 threads)
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 
@@ -80,6 +80,7 @@ struct TcParams {
   int fold;                   // bf16x3 with BN <= 128 (HDN_TC_X3FOLD, experiment): weight chunks laid out [head | tail] along N, the
                               //   accumulator is 2*BN columns wide, A_hi x [B_hi | B_lo] is ONE MMA (+ A_lo x B_hi): 2 MMAs per step
   int l2pf;                   // 1: raw patch copies carry the L2::256B prefetch hint (HDN_TC_L2PF, experiment)
+  int epi4;                   // 1: dgrad epilogue in the quad form (16-byte stores / vector reductions; HDN_TC_EPI4, default 1)
   int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
   int tail16;                 // 1: the tails of both operands are IEEE half instead of bfloat16 (HDN_TC_TAIL16; ~19 instead of ~16 significant bits)
@@ -827,7 +828,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const hdn_dgrad_epi& E = p.epi[e];
             if (E.mode == 2) continue;
             const hdn_src& S = p.esrc[e];
-            if (cok) {
+            if (p.epi4) {
+              // Quad form: lane = (row sub-index, channel quad).  A lane owns 4 consecutive channels of rows 4*it + rsub:
+              // the stored values arrive as 16-byte loads, the gradient leaves as ONE 16-byte store or vector reduction
+              // per row (red.global.add.v4.f32) instead of four 4-byte REDs -- the dense blocks' 1x1 data gradients issue
+              // ~9.5 G such elements per step and were bound by the SM's reduction issue rate, not by HBM.
+              const int rsub = lane >> 3, cq = lane & 7;
+              const int col4 = n_tile * p.BN + cb + 4 * cq;
+              const bool qok = 4 * cq < ncols && col4 < p.NC;          // NC % 8 == 0: a quad is all-in or all-out
+              float4 a4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f), c4 = b4;
+              if (qok) {
+                if (S.pa) a4 = ldg4(S.pa + col4);
+                if (S.pb) b4 = ldg4(S.pb + col4);
+                if (E.s1 && E.center) c4 = ldg4(E.center + col4);
+              }
+              const bool up_w = S.uw == 2, up_h = S.uh == 2, atom = S.ud == 2, acc = E.accumulate != 0, relu = S.relu != 0;
+              const float* xb = S.t.p;
+              float* db = E.mode == 0 ? const_cast<float*>(E.dx.p) : E.du;
+              const float4 ga = E.mode == 0 ? a4 : make_float4(1.f, 1.f, 1.f, 1.f);
+              const long long* rx = rox + e * 32;
+              const long long* rd = rod + e * 32;
+              const unsigned wm = wmask[e];
+              float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+              // two batches of 4 rows: the 4 stored-value loads of a batch are in flight together
+              for (int it0 = 0; it0 < 8; it0 += 4) {
+                float4 xs[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int rr = 4 * (it0 + k) + rsub;
+                  xs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (qok && ((wm >> rr) & 1u)) xs[k] = ldg4(xb + rx[rr] + col4);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int rr = 4 * (it0 + k) + rsub;
+                  if (!(qok && ((wm >> rr) & 1u))) continue;
+                  const float* tp = tT + rr * 33 + 4 * cq;
+                  float4 dz = make_float4(tp[0], tp[1], tp[2], tp[3]);
+                  if (up_w) { const float* t1 = tT + (rr ^ 1) * 33 + 4 * cq; dz.x += t1[0]; dz.y += t1[1]; dz.z += t1[2]; dz.w += t1[3]; }
+                  if (up_h) {
+                    const float* t8 = tT + (rr ^ 8) * 33 + 4 * cq; dz.x += t8[0]; dz.y += t8[1]; dz.z += t8[2]; dz.w += t8[3];
+                    if (up_w) { const float* t9 = tT + (rr ^ 9) * 33 + 4 * cq; dz.x += t9[0]; dz.y += t9[1]; dz.z += t9[2]; dz.w += t9[3]; }
+                  }
+                  const float4 x = xs[k];
+                  if (relu) {
+                    if (!(fmaf(a4.x, x.x, b4.x) > 0.f)) dz.x = 0.f;
+                    if (!(fmaf(a4.y, x.y, b4.y) > 0.f)) dz.y = 0.f;
+                    if (!(fmaf(a4.z, x.z, b4.z) > 0.f)) dz.z = 0.f;
+                    if (!(fmaf(a4.w, x.w, b4.w) > 0.f)) dz.w = 0.f;
+                  }
+                  s1.x += dz.x; s1.y += dz.y; s1.z += dz.z; s1.w += dz.w;
+                  s2.x += dz.x * (x.x - c4.x); s2.y += dz.y * (x.y - c4.y); s2.z += dz.z * (x.z - c4.z); s2.w += dz.w * (x.w - c4.w);
+                  float* q = db + rd[rr] + col4;
+                  const float4 g = make_float4(ga.x * dz.x, ga.y * dz.y, ga.z * dz.z, ga.w * dz.w);
+                  if (atom | acc)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
+                  else
+                    *reinterpret_cast<float4*>(q) = g;
+                }
+              }
+              if (E.s1) {                                                // (warp-uniform) fold the 4 row sub-indices of a quad
+#pragma unroll
+                for (int o = 8; o <= 16; o <<= 1) {
+                  s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                  s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+                  s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+                  s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+                }
+                if (rsub == 0 && qok) {
+                  float* p1 = &st_[(2 * e) * p.BN + cb + 4 * cq];
+                  float* p2 = &st_[(2 * e + 1) * p.BN + cb + 4 * cq];
+                  atomicAdd(p1, s1.x); atomicAdd(p1 + 1, s1.y); atomicAdd(p1 + 2, s1.z); atomicAdd(p1 + 3, s1.w);
+                  atomicAdd(p2, s2.x); atomicAdd(p2 + 1, s2.y); atomicAdd(p2 + 2, s2.z); atomicAdd(p2 + 3, s2.w);
+                }
+              }
+            } else if (cok) {
               const float a = S.pa ? __ldg(S.pa + col) : 1.f, b = S.pb ? __ldg(S.pb + col) : 0.f;
               const float ctr = (E.s1 && E.center) ? __ldg(E.center + col) : 0.f;
               const bool up_w = S.uw == 2, up_h = S.uh == 2, atom = S.ud == 2, acc = E.accumulate != 0, relu = S.relu != 0;
@@ -1240,6 +1315,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.split = nsplit == 2 ? 1 : 0;
   p.tail16 = tail16;
   p.fastx = hdn_tc_fastx();
+  { static int v = -1; if (v < 0) { const char* e = getenv("HDN_TC_EPI4"); v = (e && atoi(e) == 0) ? 0 : 1; } p.epi4 = v; }
   p.l2pf = hdn_tc_l2pf();
   p.fold = pl.fold;
   if (mode == 0) {

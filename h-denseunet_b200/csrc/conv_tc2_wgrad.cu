@@ -461,13 +461,14 @@ int hdn_wgrad_tc2_enabled() {
 void hdn_wgrad_tc2_set(int v) { g_wgrad_tc2 = v ? 1 : 0; }
 void hdn_tc2_layout_set(int v) { g_layout = v ? 1 : 0; }
 
-// shapes the tc2 weight gradient takes: plain bf16 operands (precision 1), stride-1 "same" 1x3x3 / 3x3x3
+// shapes the tc2 weight gradient takes: plain bf16 operands (precision 1), stride-1 "same" 1x1x1 / 1x3x3 / 3x3x3
 int hdn_wgrad_tc2_supported(const hdn_conv* c) {
   if (c->precision != 1 || hdn_tc_stem(c)) return 0;
   if (c->sd != 1 || c->sh != 1 || c->sw != 1) return 0;
+  const bool k111 = c->kd == 1 && c->kh == 1 && c->kw == 1;
   const bool k133 = c->kd == 1 && c->kh == 3 && c->kw == 3;
   const bool k333 = c->kd == 3 && c->kh == 3 && c->kw == 3;
-  if (!(k133 || k333)) return 0;
+  if (!(k111 || k133 || k333)) return 0;
   if (c->pd != c->kd / 2 || c->ph != c->kh / 2 || c->pw != c->kw / 2) return 0;
   const hdn_src& s0 = c->src[0];
   if (c->D != s0.D * s0.ud || c->H != s0.H * s0.uh || c->W != s0.W * s0.uw) return 0;

@@ -29,6 +29,11 @@ from . import _lib
 #              weight gradients (a leaf: their rounding error stays in that one tensor, ~3e-3) on plain bf16 operands
 TC_PRECISION = {"bf16": (1, 1, 1), "bf16x3": (2, 2, 2), "mixed": (2, 2, 1)}
 
+# HDN_POISON=1 (debug aid): activation / gradient buffers start as NaN instead of uninitialised memory, so that a read of an
+# element no kernel has written shows up in the results (fresh CUDA pages are zero: such reads hide in a new process)
+import os as _os
+POISON = _os.environ.get("HDN_POISON", "0") not in ("", "0")
+
 
 # ------------------------------------------------------------------------- descriptors
 class TView(object):
@@ -61,6 +66,8 @@ class Buffer(object):
         self.net, self.name = net, name
         self.N, self.D, self.H, self.W, self.C = N, D, H, W, C_
         self.data = torch.empty((N, D, H, W, C_), dtype=torch.float32, device=net.device)
+        if POISON and self.data.device.type == "cuda":
+            self.data.fill_(float("nan"))      # HDN_POISON=1: a kernel that consumes a never-written element turns the result into NaN
         self.grad = None
         self.requires_grad = False
         self.need_stats = np.zeros(C_, bool)
@@ -73,6 +80,8 @@ class Buffer(object):
     def ensure_grad(self):
         if self.grad is None:
             self.grad = torch.empty_like(self.data)
+            if POISON and self.grad.device.type == "cuda":
+                self.grad.fill_(float("nan"))
         return self.grad
 
 
@@ -912,6 +921,8 @@ class Net(object):
             for op in reversed(self.ops):
                 op.plan_backward(planner)
             self.scratch = torch.empty(max(planner.top, 4), dtype=torch.float32, device=self.device)
+            if POISON and self.device.type == "cuda":
+                self.scratch.fill_(float("nan"))
             for op in self.ops:
                 for e in getattr(op, "epis", []) + ([op.epi] if hasattr(op, "epi") else []):
                     if isinstance(e.du, tuple):

@@ -231,11 +231,14 @@ def test_wgrad_tc_vs_fp32(cuda_dev, name, prec):
 
 # ---- second-generation weight gradient (conv_tc2_wgrad.cu: bf16 pre-pass + TMA tile loads + tcgen05) ---------------
 W2 = ["3x3_dense", "3x3x3_dense", "3x3_up_skip_bias_stats", "3x3x3_up222_bias_stats", "3x3x3_up122_504", "3x3_wide",
-      "3x3x3_two_src"]
+      "3x3x3_two_src", "1x1_flat", "1x1_flat_tail"]
 W2_EXTRA = {
     # ragged grid (H, W not multiples of the 16 x 8 tile), channel tails inside a 128-channel tile / a 64-channel block
     "3x3x3_ragged": dict(N=2, D=3, H=20, W=12, cin=96, cout=64, k=(3, 3, 3), bias=True),
     "3x3_ragged_c200": dict(N=1, D=2, H=24, W=20, cin=200, cout=72, k=(1, 3, 3)),
+    # 1x1x1: flat position tiles (2-D tensor map), M not a multiple of 128, a transition-like shape with many channel tiles
+    "1x1_flat_m_tail": dict(N=3, D=1, H=13, W=11, cin=1200, cout=192, k=(1, 1, 1)),
+    "1x1_up_two_src": dict(N=1, D=2, H=16, W=16, cin=64, cout=40, k=(1, 1, 1), ups=((1, 1, 1), (2, 2, 2)), fold=(False, True), bias=True),
 }
 
 

@@ -57,7 +57,7 @@ def test_every_convolution_has_a_valid_plan(plan_rows, prec):
                 assert prec == 1 and P in (180, 160, 128) and 2 <= nraw <= 6, what
                 assert ws % 256 == 0, what
             else:
-                assert prec == 2 or P == 128 or s2d, what          # gen 1 keeps bf16x3, the 1x1x1 layers and the stems
+                assert prec == 2 or s2d, what                      # gen 1 keeps bf16x3 and the stems
 
 
 def test_bf16x3_workspace_is_twice_the_bf16_one_per_channel_block(plan_rows):

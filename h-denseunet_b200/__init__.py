@@ -13,7 +13,9 @@ from .builders import (DenseUNet, DenseUNet161, DenseUNet3d, DenseNet3D, dense_r
 from .keras_api import (Model, SGD, ModelCheckpoint, make_parallel, weighted_crossentropy,
                         weighted_crossentropy_2ddense)
 from .inference import predict_tumor_inwindow
+from .postprocess import postprocess_scores
+from . import keras_api, keras_h5, h5lite, preprocessing
 
 __all__ = ["DenseUNet", "DenseUNet161", "DenseUNet3d", "DenseNet3D", "dense_rnn_net", "denseunet_3d", "Scale",
            "Model", "SGD", "ModelCheckpoint", "make_parallel", "weighted_crossentropy",
-           "weighted_crossentropy_2ddense", "predict_tumor_inwindow"]
+           "weighted_crossentropy_2ddense", "predict_tumor_inwindow", "postprocess_scores"]

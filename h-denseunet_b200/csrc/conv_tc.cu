@@ -24,9 +24,14 @@
 //   warp 9     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
 //              TMEM accumulator buffers and releases stages with tcgen05.commit.
 //   warps 10-13 epilogue: tcgen05.ld the finished accumulator while the next tile's MMAs run.
+#include <cuda.h>
 #include <stdlib.h>
 #include "hdn_common.cuh"
 #include "tc_common.cuh"
+
+// shared with the tc2 weight gradient (conv_tc2_wgrad.cu): bf16 operand pre-pass and tensor maps over its output
+int hdn_tc2_make_map(CUtensorMap* tm, const void* base, int flat, long long M, int N, int D, int H, int W, int C, int bc, int bw, int bh);
+int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
 // -DHDN_TC_TIMING: per-role wait/work cycle counters of CTA 0, printed at kernel end (development aid)
 #ifdef HDN_TC_TIMING
@@ -51,7 +56,8 @@ constexpr bool kFold = false;
 
 constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
 constexpr int NPROD = 256;        // producer threads
-constexpr int NSA = 2;        // bf16 A-operand stages
+constexpr int NSA = 2;        // bf16 A-operand stages of the SIMT-producer form
+constexpr int MAXNSA = 6;     // ... upper bound (TMA mode: TcParams::nsa stages)
 constexpr int NSB_MAX = 16;   // weight-block ring depth upper bound
 constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs at most 3 stages ahead of the transform)
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
@@ -61,6 +67,10 @@ constexpr int MAXC0 = 14;     // copies per producer thread and stage, source 0 
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 
 struct TcParams {
+  CUtensorMap tmHi, tmLo;     // TMA mode: bf16 head / tail tensors of the A operand on the virtual grid (C, W, H, D, N) or flat (C, M)
+  int tma;                    // 1: the A operand was pre-packed to bf16 by hdn_tc2_pack and is staged by TMA tile loads (one box
+                              //    {8 channels, PW, PH} per chunk plane; out-of-bounds = the zero padding); no SIMT producers
+  int nsa;                    // A-operand stages in the ring (2 in the SIMT-producer form)
   int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
   int kd, kh, kw;
   int K, NC;                  // contraction channels, output columns
@@ -199,23 +209,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t A_BYTES = 8u * p.Ppad * 16u;
   const uint32_t B_HALF = (uint32_t)p.BN * (uint32_t)p.CK * 2u;          // one bf16 weight block
   const uint32_t B_BYTES = p.split ? 2u * B_HALF : B_HALF;                 // bf16x3: head block | tail block
+  const int nsa = p.nsa;
   uint8_t* sA = smem;
-  uint8_t* sB = sA + NSA * A_BYTES;
+  uint8_t* sB = sA + nsa * A_BYTES;
   uint8_t* sRaw = sB + p.nsb * B_BYTES;
   int* tabs = reinterpret_cast<int*>(sRaw + (size_t)p.nraw * p.raw_bytes);
   float* sstat = reinterpret_cast<float*>(tabs + NTAB * p.tab_ints);        // [2 buffers][4][BN]
   uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 15) & ~uintptr_t(15));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * EPI_BYTES);
   uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + NSA;
-  uint64_t* b_full = a_empty + NSA;
+  uint64_t* a_empty = a_full + MAXNSA;
+  uint64_t* b_full = a_empty + MAXNSA;
   uint64_t* b_empty = b_full + NSB_MAX;
   uint64_t* acc_full = b_empty + NSB_MAX;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < NSA; ++i) { tc::mbar_init(&a_full[i], NPROD); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < MAXNSA; ++i) { tc::mbar_init(&a_full[i], p.tma ? 1 : NPROD); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB_MAX; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
@@ -284,7 +295,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     int sa = 0;
     uint32_t pha = 0;
 
-    if (!p.s2d) {
+    if (p.tma) {
+      // ---- TMA mode: the operand is already bf16 in global memory; warp 0 (converged, one elected lane issuing) stages one
+      // chunk plane per box.  Zero padding, image borders and channel tails are the copy engine's out-of-bounds fill.
+      if (warp == 0) {
+        if (tc::elect_one_sync()) { tc::tma_prefetch_desc(&p.tmHi); if (p.split) tc::tma_prefetch_desc(&p.tmLo); }
+        const uint32_t plane = (uint32_t)p.Ppad * 16u;
+        const uint32_t box_bytes = (uint32_t)p.P * 16u;
+        while (!tr.done) {
+          tc::mbar_wait(&a_empty[sa], pha ^ 1);
+          if (tc::elect_one_sync()) {
+            uint8_t* dst = sA + sa * A_BYTES;
+            const int c0 = tr.kb * p.CK;
+            tc::mbar_arrive_expect_tx(&a_full[sa], 8u * box_bytes);
+            const int nhi = p.split ? 4 : 8;
+            if (p.flat) {
+              for (int j = 0; j < nhi; ++j) tc::tma_load_2d(dst + j * plane, &p.tmHi, &a_full[sa], c0 + 8 * j, (int)tr.t.m0);
+              if (p.split)
+                for (int j = 0; j < 4; ++j) tc::tma_load_2d(dst + (4 + j) * plane, &p.tmLo, &a_full[sa], c0 + 8 * j, (int)tr.t.m0);
+            } else {
+              const int aw = tr.t.w0 - p.pw_lo, ah = tr.t.h0 - p.ph_lo, ad = tr.t.d0 - p.pd_lo + tr.dz;
+              for (int j = 0; j < nhi; ++j) tc::tma_load_5d(dst + j * plane, &p.tmHi, &a_full[sa], c0 + 8 * j, aw, ah, ad, tr.t.n_img);
+              if (p.split)
+                for (int j = 0; j < 4; ++j) tc::tma_load_5d(dst + (4 + j) * plane, &p.tmLo, &a_full[sa], c0 + 8 * j, aw, ah, ad, tr.t.n_img);
+            }
+          }
+          __syncwarp();
+          if (++sa == nsa) { sa = 0; pha ^= 1; }
+          it_next(p, tr);
+        }
+      }
+    } else if (!p.s2d) {
       // ---- asynchronous path: raw fp32 patch -> shared memory with cp.async, several stages ahead
       StageIt is;
       it_init(p, is);
@@ -467,7 +508,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[sa]);
-        if (++sa == NSA) { sa = 0; pha ^= 1; }
+        if (++sa == nsa) { sa = 0; pha ^= 1; }
         if (++slot_tr == p.nraw) slot_tr = 0;
         it_next(p, tr);
         TT_ADD(t_xform);
@@ -521,7 +562,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a_full[sa]);
-        if (++sa == NSA) { sa = 0; pha ^= 1; }
+        if (++sa == nsa) { sa = 0; pha ^= 1; }
         it_next(p, tr);
       }
     }
@@ -633,7 +674,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         const int seq_before = it.seq;
         const int sa_done = sa;
-        if (++sa == NSA) { sa = 0; pha ^= 1; }
+        if (++sa == nsa) { sa = 0; pha ^= 1; }
         it_next(p, it);
         if (tc::elect_one_sync()) {
           tc::umma_commit(&a_empty[sa_done]);
@@ -1123,6 +1164,19 @@ int hdn_tc_x3fold() {
 // The code path is kept behind this constant for the record; it is never enabled.
 int hdn_tc_tail16() { return 0; }
 
+// HDN_TC_TMA: which fprop / dgrad launches take the TMA mode (bf16 operand pre-pass + tile loads instead of the SIMT
+// producers): 0 none, 1 the 1x3x3 / 3x3x3 layers (default), 2 also the 1x1x1 layers.  Stems keep their own producer.
+static int g_tc_tma = -1;
+int hdn_tc_tma() {
+  if (g_tc_tma < 0) {
+    const char* e = getenv("HDN_TC_TMA");
+    g_tc_tma = e ? atoi(e) : 1;
+    if (g_tc_tma < 0 || g_tc_tma > 2) g_tc_tma = 1;
+  }
+  return g_tc_tma;
+}
+void hdn_tc_tma_set(int v) { g_tc_tma = v < 0 ? 0 : (v > 2 ? 2 : v); }
+
 // HDN_TC_L2PF=1: experiment switch, see TcParams::l2pf (default 0)
 int hdn_tc_l2pf() {
   static int v = -1;
@@ -1136,6 +1190,8 @@ int hdn_tc_l2pf() {
 namespace {
 
 struct TcPlan {
+  int tma, nsa;                     // TMA mode (pre-packed bf16 operand), A-ring depth
+  long long op_elems;               // bf16 elements of one pre-packed operand tensor (head; the tail doubles it)
   int fold;
   int BN, n_tiles, KB, CK, nsb, nraw, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
   int PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], raw_bytes, tab_src[2], tab_vq[2], tab_ints;
@@ -1207,18 +1263,22 @@ TcGeom tc_geom(const hdn_conv* c, int mode) {
 TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   TcPlan pl;
   memset(&pl, 0, sizeof(pl));
+  const int tma_level = hdn_tc_tma();
+  pl.tma = (!g.s2d && !g.scatter && (long long)c->N * c->D * c->H * c->W < (1ll << 31) &&
+            (tma_level >= 2 || (tma_level == 1 && !g.flat))) ? 1 : 0;
+  pl.nsa = NSA;
   const int nsplit = c->precision == 2 ? 2 : 1;           // bf16x3: head + tail of every operand
   pl.n_tiles = (g.NC + 255) / 256 + extra_tiles;
   int bn = (g.NC + pl.n_tiles - 1) / pl.n_tiles;
   pl.BN = (bn + 15) / 16 * 16;
   const int nsrc = mode == 0 ? c->nsrc : 1;               // dgrad: the A operand is dY alone
-  pl.CK = (nsrc == 2 || nsplit == 2) ? 32 : 64;           // channels per stage (two raw patches, or head + tail chunks, must fit a stage)
+  pl.CK = ((nsrc == 2 && !pl.tma) || nsplit == 2) ? 32 : 64;   // channels per stage (two raw patches, or head + tail chunks, must fit a stage)
   pl.KB = (g.K + pl.CK - 1) / pl.CK;
   pl.flat = g.flat;
   pl.PH = 16 + g.kh - 1;
   pl.PW = 8 + g.kw - 1;
   pl.P = pl.PH * pl.PW;
-  pl.Ppad = pl.P | 1;
+  pl.Ppad = pl.tma ? (pl.P + 7) / 8 * 8 : (pl.P | 1);       // TMA planes start on 128-byte boundaries
   pl.tiles_h = (c->H + 15) / 16;
   pl.tiles_w = (c->W + 7) / 8;
   int off = 0, toff = 0;
@@ -1243,9 +1303,25 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   while (cols < 2 * pl.BN * (pl.fold ? 2 : 1)) cols *= 2;  // two accumulator buffers
   pl.tmem_cols = cols;
   pl.ws_elems = (long long)pl.n_tiles * pl.KB * (g.kd * g.kh * g.kw) * pl.BN * pl.CK * nsplit;
-  const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES +
-                      (2 * NSA + 2 * NSB_MAX + 4) * 8 + 16;
   const long long budget = 226 * 1024;
+  if (pl.tma) {
+    // no raw ring, no geometry tables: the A ring gets up to 4 stages next to >= taps_hw (<= 12) weight blocks
+    pl.tab_ints = 0; pl.raw_bytes = 0;
+    const size_t fix = 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128;
+    const int want_b = g.kh * g.kw < 4 ? 4 : (g.kh * g.kw > 12 ? 12 : g.kh * g.kw);
+    int nsa = 4;
+    while (nsa > 2 && (long long)(fix + nsa * a_bytes + (size_t)want_b * b_bytes) > budget) --nsa;
+    pl.nsa = nsa;
+    long long room = budget - (long long)fix - (long long)nsa * (long long)a_bytes;
+    int nsb = (int)(room / (long long)b_bytes);
+    pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
+    pl.nraw = (room >= 2 * (long long)b_bytes) ? nsa : 0;      // reported in the plan's ring-depth slot; 0 = does not fit (narrower tile)
+    pl.smem = fix + (size_t)nsa * a_bytes + (size_t)pl.nsb * b_bytes;
+    pl.op_elems = (long long)c->N * c->D * c->H * c->W * g.K;
+    return pl;
+  }
+  const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES +
+                      (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16;
   // raw fp32 ring: 3 stages when they fit next to two weight blocks, else 2; the weight ring takes what is left:
   // every tile streams ALL its weight blocks from L2, so the bytes in flight there set the pace of narrow layers
   pl.nraw = 0;
@@ -1273,7 +1349,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   const TcPlan pl = tc_plan(c, g, mode);
   const int nsplit = c->precision == 2 ? 2 : 1;
   HDN_CHECK_ARG(g.s2d || pl.nraw >= 2, "conv tc: shared memory cannot hold two raw stages (BN=%d)", pl.BN);
-  HDN_CHECK_ARG(g.s2d || (pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD),
+  HDN_CHECK_ARG(g.s2d || pl.tma || (pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD),
                 "conv tc: patch of %d / %d pixels exceeds the per-thread copy list", pl.Ps[0], pl.Ps[1]);
   HDN_CHECK_ARG(c->ws != nullptr && c->ws_bytes >= pl.ws_elems * 2, "conv tc: workspace too small (%lld < %lld bytes)",
                 (long long)c->ws_bytes, (long long)pl.ws_elems * 2);
@@ -1283,6 +1359,11 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     if (e != cudaSuccess) { hdn_set_error("conv tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
     attr_set = true;
   }
+  const long long w_bytes = (pl.ws_elems * 2 + 255) / 256 * 256;
+  const long long op_bytes = pl.tma ? (pl.op_elems * 2 + 255) / 256 * 256 : 0;
+  HDN_CHECK_ARG(!pl.tma || (c->ws_bytes >= w_bytes + op_bytes * nsplit && (reinterpret_cast<uintptr_t>(c->ws) & 255) == 0),
+                "conv tc: workspace too small or misaligned for the pre-packed operand (%lld < %lld bytes)", (long long)c->ws_bytes,
+                (long long)(w_bytes + op_bytes * nsplit));
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(c->ws);
   const int tail16 = (nsplit == 2 && !pl.fold && hdn_tc_tail16()) ? 1 : 0;
   {
@@ -1296,6 +1377,25 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.tma = pl.tma; p.nsa = pl.nsa;
+  if (pl.tma) {
+    // operand pre-pass (once per launch): fprop -- max(a*x+b, 0) (+ second source) on the virtual grid; dgrad -- dY
+    __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(c->ws) + w_bytes);
+    __nv_bfloat16* lo = nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(c->ws) + w_bytes + op_bytes) : nullptr;
+    int rc;
+    if (mode == 0) rc = hdn_tc2_pack(c->src, c->nsrc, c->N, c->D, c->H, c->W, c->Cin, hi, lo, st);
+    else {
+      hdn_src dys;
+      memset(&dys, 0, sizeof(dys));
+      dys.t = c->y; dys.D = c->D; dys.H = c->H; dys.W = c->W; dys.ud = dys.uh = dys.uw = 1;
+      rc = hdn_tc2_pack(&dys, 1, c->N, c->D, c->H, c->W, c->Cout, hi, lo, st);
+    }
+    if (rc) return rc;
+    const long long Mv = (long long)c->N * c->D * c->H * c->W;
+    rc = hdn_tc2_make_map(&p.tmHi, hi, pl.flat, Mv, c->N, c->D, c->H, c->W, g.K, 8, pl.PW, pl.PH);
+    if (rc) return rc;
+    if (lo) { rc = hdn_tc2_make_map(&p.tmLo, lo, pl.flat, Mv, c->N, c->D, c->H, c->W, g.K, 8, pl.PW, pl.PH); if (rc) return rc; }
+  }
   p.N = c->N; p.D = c->D; p.H = c->H; p.W = c->W;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw;
   p.pd_lo = g.pd_lo; p.ph_lo = g.ph_lo; p.pw_lo = g.pw_lo;
@@ -1390,7 +1490,10 @@ int hdn_tc_supported(const hdn_conv* c, int pass) {
 
 long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
   if (!hdn_tc_supported(c, pass) || pass == 2) return 0;
-  return tc_plan(c, tc_geom(c, pass), pass).ws_elems * 2;
+  const TcPlan pl = tc_plan(c, tc_geom(c, pass), pass);
+  const long long w_bytes = (pl.ws_elems * 2 + 255) / 256 * 256;
+  if (!pl.tma) return pl.ws_elems * 2;
+  return w_bytes + (pl.op_elems * 2 + 255) / 256 * 256 * (c->precision == 2 ? 2 : 1);      // packed weights + bf16 head (+ tail) operand
 }
 
 // launch plan of the fprop / dgrad kernel for this descriptor (host arithmetic only; see hdn_conv_tc_plan in hdn.h)
@@ -1402,7 +1505,7 @@ int hdn_tc_plan_info(const hdn_conv* c, int pass, int* out) {
   out[0] = pl.BN; out[1] = pl.n_tiles; out[2] = pl.KB; out[3] = pl.CK; out[4] = pl.nsb; out[5] = pl.nraw;
   out[6] = pl.tmem_cols; out[7] = (int)pl.smem; out[8] = pl.flat; out[9] = pl.P; out[10] = c->precision == 2 ? 1 : 0;
   out[11] = g.s2d; out[12] = (tiles * pl.n_tiles < (1ll << 31)) ? (int)(tiles * pl.n_tiles) : -1;
-  out[13] = pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD;   // per-thread copy list holds the patch
+  out[13] = pl.tma || (pl.Ps[0] * (pl.CK / 4) <= MAXC0 * NPROD && pl.Ps[1] * (pl.CK / 4) <= MAXC1 * NPROD);   // per-thread copy list holds the patch (SIMT-producer form)
   out[14] = g.K; out[15] = g.NC;
   return HDN_OK;
 }

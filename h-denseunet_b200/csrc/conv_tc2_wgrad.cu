@@ -274,6 +274,7 @@ struct PackParams {
   int D, H, W, C, nsrc;
   hdn_src src[2];
   __nv_bfloat16* out;
+  __nv_bfloat16* out_lo;              // optional: bf16 tail x - bf16(x) (the second operand term of bf16x3)
   long long total;                    // pixels * (C / 8)
 };
 
@@ -306,8 +307,15 @@ __global__ void __launch_bounds__(256) act_pack_bf16_kernel(const __grid_constan
       v0.x += x0.x; v0.y += x0.y; v0.z += x0.z; v0.w += x0.w; v1.x += x1.x; v1.y += x1.y; v1.z += x1.z; v1.w += x1.w;
     }
     uint4 o;
-    o.x = tc::pack_bf16x2(v0.x, v0.y); o.y = tc::pack_bf16x2(v0.z, v0.w);
-    o.z = tc::pack_bf16x2(v1.x, v1.y); o.w = tc::pack_bf16x2(v1.z, v1.w);
+    if (p.out_lo) {
+      uint4 t;
+      tc::pack_split_bf16x2(v0.x, v0.y, o.x, t.x); tc::pack_split_bf16x2(v0.z, v0.w, o.y, t.y);
+      tc::pack_split_bf16x2(v1.x, v1.y, o.z, t.z); tc::pack_split_bf16x2(v1.z, v1.w, o.w, t.w);
+      reinterpret_cast<uint4*>(p.out_lo)[idx] = t;
+    } else {
+      o.x = tc::pack_bf16x2(v0.x, v0.y); o.y = tc::pack_bf16x2(v0.z, v0.w);
+      o.z = tc::pack_bf16x2(v1.x, v1.y); o.w = tc::pack_bf16x2(v1.z, v1.w);
+    }
     reinterpret_cast<uint4*>(p.out)[idx] = o;
   }
 }
@@ -433,12 +441,14 @@ bool wg2_plan(const hdn_conv* c, Wg2Plan& best) {
   return true;
 }
 
-int pack_launch(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* out, cudaStream_t st) {
+int pack_launch(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* out, cudaStream_t st,
+                __nv_bfloat16* out_lo = nullptr) {
   PackParams pp;
   memset(&pp, 0, sizeof(pp));
   pp.D = D; pp.H = H; pp.W = W; pp.C = C; pp.nsrc = nsrc;
   for (int i = 0; i < nsrc; ++i) pp.src[i] = srcs[i];
   pp.out = out;
+  pp.out_lo = out_lo;
   pp.total = (long long)N * D * H * W * (C / 8);
   const long long blocks = (pp.total + 255) / 256;
   const unsigned grid = (unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks);
@@ -448,6 +458,14 @@ int pack_launch(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C
 }
 
 }  // namespace
+
+// shared with the fprop / dgrad kernel's TMA mode (conv_tc.cu)
+int hdn_tc2_make_map(CUtensorMap* tm, const void* base, int flat, long long M, int N, int D, int H, int W, int C, int bc, int bw, int bh) {
+  return make_map(tm, base, flat, M, N, D, H, W, C, bc, bw, bh, 0);
+}
+int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
+  return pack_launch(srcs, nsrc, N, D, H, W, C, hi, st, lo);
+}
 
 // HDN_WGRAD_TC2=0 keeps the first-generation weight-gradient kernel for every shape (default 1)
 static int g_wgrad_tc2 = -1;

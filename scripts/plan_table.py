@@ -55,11 +55,11 @@ def plans(precision, **kw):
         for ps in range(3):
             o = (C.c_int32 * 16)()
             if not lib.hdn_conv_tc_supported(C.byref(c), ps):
-                rows.append((name, ps, None, 0))
+                rows.append((name, ps, None, 0, 0))
                 continue
             rc = lib.hdn_conv_tc_plan(C.byref(c), ps, o)
             assert rc == 0, (name, ps, lib.hdn_last_error())
-            rows.append((name, ps, list(o), int(lib.hdn_conv_tc_workspace(C.byref(c), ps))))
+            rows.append((name, ps, list(o), int(lib.hdn_conv_tc_workspace(C.byref(c), ps)), int(c.N) * c.D * c.H * c.W))
     return rows
 
 
@@ -67,7 +67,7 @@ if __name__ == "__main__":
     prec = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     seen = set()
     print("%-22s pass  BN tiles KB/ci CK/CW nsb/G nraw tmem   smem flat   P x3 s2d    work fit  K/BNe NC/CI      ws" % "conv")
-    for name, ps, o, ws in plans(prec):
+    for name, ps, o, ws, _m in plans(prec):
         key = (ps, tuple(o) if o else None)
         if key in seen:
             continue

@@ -272,3 +272,36 @@ def test_wgrad_tc2_vs_fp32_and_gen1(cuda_dev, name, layout):
     assert rel_l2(w2, w1) < 1e-4, (name, rel_l2(w2, w1))
     if b0 is not None:
         assert rel_l2(b2, b0) < 1e-4
+
+
+# ---- fprop / dgrad producer forms: HDN_TC_TMA 0 = SIMT producers everywhere, 1 = TMA mode for the 1x3x3 / 3x3x3 layers
+# (default; the tests above run in it), 2 = TMA mode for the 1x1x1 layers as well -----------------------------------------
+TMA_CASES = ["1x1_flat", "1x1_flat_tail", "3x3_dense", "3x3x3_dense", "3x3_up_skip_bias_stats", "3x3x3_up222_bias_stats",
+             "3x3x3_up122_504", "3x3x3_two_src", "3x3_wide"]
+
+
+@pytest.mark.parametrize("level", [0, 2])
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", TMA_CASES)
+def test_fprop_dgrad_producer_forms(cuda_dev, name, prec, level):
+    kw = dict(CASES[name])
+    kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
+    _switch("HDN_TC_TMA", level)
+    try:
+        c = Case(cuda_dev, tc=prec, **kw)
+        TOL = TOLS[prec]
+        y0, s0, _ = c.fprop(0)
+        y1, s1, untouched = c.fprop(prec)
+        assert untouched == 0.0
+        assert rel_l2(y1, y0) < TOL, (name, rel_l2(y1, y0))
+        if s0 is not None:
+            assert rel_l2(s1[0], s0[0]) < TOL and rel_l2(s1[1], s0[1]) < TOL
+        if name in DG:
+            for mode, acc in ((0, False), (0, True), (1, True)):
+                r0 = c.dgrad(0, mode, acc)
+                r1 = c.dgrad(prec, mode, acc)
+                for (g0, S0), (g1, S1) in zip(r0, r1):
+                    assert rel_l2(g1, g0) < TOL, (name, mode, acc, rel_l2(g1, g0))
+                    assert rel_l2(S1[0], S0[0]) < TOL and rel_l2(S1[1], S0[1]) < TOL
+    finally:
+        _switch("HDN_TC_TMA", 1)

@@ -26,11 +26,11 @@ def plan_rows():
 def test_every_convolution_has_a_valid_plan(plan_rows, prec):
     rows = plan_rows[prec]
     assert len(rows) == 3 * 231                                  # 231 convolutions x 3 passes
-    fallbacks = [(n, ps) for n, ps, o, _ in rows if o is None]
+    fallbacks = [(n, ps) for n, ps, o, _, _ in rows if o is None]
     # only the two 3-class classifiers' dgrad / wgrad (Cout = 3) stay on the fp32 FMA kernels
     assert sorted(fallbacks) == sorted([("dense167classifer", 1), ("dense167classifer", 2),
                                         ("2d3dclassifer", 1), ("2d3dclassifer", 2)]), fallbacks
-    for name, ps, o, ws in rows:
+    for name, ps, o, ws, M in rows:
         if o is None:
             continue
         bn, tiles, kb, ck, ring, nraw, tmem, smem, flat, P, x3, s2d, work, fit, k_or_bne, nc_or_ci = o
@@ -43,9 +43,16 @@ def test_every_convolution_has_a_valid_plan(plan_rows, prec):
         if ps < 2:
             assert 2 * bn <= tmem, what                            # two accumulator buffers
             assert ring >= 2, what                                 # weight ring
-            assert s2d or nraw >= 2, what                          # raw fp32 ring of the asynchronous producer
+            assert s2d or nraw >= 2, what                          # raw fp32 ring (SIMT producers) / A-stage ring (TMA mode)
             assert ck == (32 if prec == 2 else ck) and ck in (32, 64), what
-            assert ws > 0 and ws % (bn * ck * 2 * (2 if prec == 2 else 1)) == 0, what
+            nsplit = 2 if prec == 2 else 1
+            wbytes = tiles * kb * bn * ck * 2 * nsplit
+            assert ws > 0 and (ws % (bn * ck * 2 * nsplit) == 0 or ws > wbytes), what
+            if P == 180:
+                # TMA mode (default for the 1x3x3 / 3x3x3 layers): packed weights + the pre-packed bf16 head (+ tail) operand
+                k = k_or_bne
+                opb = (M * k * 2 + 255) // 256 * 256
+                assert ws >= opb * nsplit and (ws - opb * nsplit) % 256 == 0, what
         else:
             bne, ci = k_or_bne, nc_or_ci
             assert bne == bn * (2 if prec == 2 else 1) and bne <= 256, what
@@ -62,8 +69,9 @@ def test_every_convolution_has_a_valid_plan(plan_rows, prec):
 
 def test_bf16x3_workspace_is_twice_the_bf16_one_per_channel_block(plan_rows):
     """bf16x3 packs a head and a tail block per (column tile, K block, tap): same bytes per covered channel x2."""
-    a = {(n, ps): (o, ws) for n, ps, o, ws in plan_rows[1] if o is not None and ps < 2}
-    b = {(n, ps): (o, ws) for n, ps, o, ws in plan_rows[2] if o is not None and ps < 2}
+    # (layers in the SIMT-producer form: stems and 1x1x1; the TMA-mode layers add their operand tensors to the scratch)
+    a = {(n, ps): (o, ws) for n, ps, o, ws, _ in plan_rows[1] if o is not None and ps < 2 and (o[8] or o[11])}
+    b = {(n, ps): (o, ws) for n, ps, o, ws, _ in plan_rows[2] if o is not None and ps < 2 and (o[8] or o[11])}
     assert a.keys() == b.keys()
     for key in a:
         (o1, w1), (o2, w2) = a[key], b[key]

@@ -336,6 +336,156 @@ __global__ void __launch_bounds__(256) conv_wgrad_small_n(const hdn_conv c, floa
   }
 }
 
+// Classifier-shaped 1x1x1 convolutions (Cout <= 4: dense167classifer / 2d3dclassifer, hybridnet.py:260,419), vector forms.
+// Both passes are HBM-bound column work over M positions x Cin channels; thread = (position lane, channel quad), so a
+// position's Cin channels are read as contiguous 16-byte pieces and every thread keeps UNR positions in flight.
+// wgrad: dw[ci][co] += sum_pos max(a*x+b,0)[pos][ci] * dY[pos][co]
+template <int UNR>
+__global__ void __launch_bounds__(256) conv_wgrad_small_n4(const hdn_conv c, float* __restrict__ dw, const int64_t M, const int nq) {
+  __shared__ float red[256 * 16];
+  const hdn_src& s = c.src[0];
+  const int q = threadIdx.x % nq, pl = threadIdx.x / nq, lanes = 256 / nq;
+  const int ci = q * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  if (pl < lanes) {
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s.pa) a = __ldg(reinterpret_cast<const float4*>(s.pa + ci));
+    if (s.pb) b = __ldg(reinterpret_cast<const float4*>(s.pb + ci));
+    const int64_t stride = (int64_t)gridDim.x * lanes;
+    for (int64_t m0 = (int64_t)blockIdx.x * lanes + pl; m0 < M; m0 += stride * UNR) {
+      float4 x[UNR];
+      float dy[UNR][4];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t m = m0 + u * stride;
+        x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dy[u][j] = 0.f;
+        if (m < M) {
+          x[u] = __ldg(reinterpret_cast<const float4*>(s.t.p + m * s.t.ldc + s.t.coff + ci));
+          const float* d = c.y.p + m * c.y.ldc + c.y.coff;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < c.Cout) dy[u][j] = __ldg(d + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (m0 + u * stride >= M) break;
+        float v[4] = {fmaf(a.x, x[u].x, b.x), fmaf(a.y, x[u].y, b.y), fmaf(a.z, x[u].z, b.z), fmaf(a.w, x[u].w, b.w)};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (s.relu) v[i] = fmaxf(v[i], 0.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(v[i], dy[u][j], acc[i][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[threadIdx.x * 16 + i * 4 + j] = acc[i][j];
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += red[(l * nq + q) * 16 + i * 4 + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < c.Cout; ++j) atomicAdd(dw + (int64_t)(ci + i) * c.Cout + j, acc[i][j]);
+  }
+}
+
+// dgrad: dz[pos][ci] = sum_co dY[pos][co] * w[ci][co], then the epilogue of hdn_dgrad_epi (ReLU mask from the stored value,
+// S1 / S2 sums, dx (+)= a*du or du (+)= du).  The quad's 4 x Cout weights and its (a, b, center) stay in registers.
+template <int UNR>
+__global__ void __launch_bounds__(256) conv_dgrad_small_n4(const hdn_conv c, const hdn_dgrad_epi e, const int64_t M, const int nq) {
+  __shared__ float red[256 * 8];
+  const hdn_src& s = c.src[0];
+  const int q = threadIdx.x % nq, pl = threadIdx.x / nq, lanes = 256 / nq;
+  const int ci = q * 4;
+  float p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pl < lanes) {
+    float4 a = make_float4(1.f, 1.f, 1.f, 1.f), b = make_float4(0.f, 0.f, 0.f, 0.f), ctr = b;
+    if (s.pa) a = __ldg(reinterpret_cast<const float4*>(s.pa + ci));
+    if (s.pb) b = __ldg(reinterpret_cast<const float4*>(s.pb + ci));
+    if (e.s1 && e.center) ctr = __ldg(reinterpret_cast<const float4*>(e.center + ci));
+    float w[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[i][j] = j < c.Cout ? __ldg(c.w + (int64_t)(ci + i) * c.Cout + j) : 0.f;
+    const int64_t stride = (int64_t)gridDim.x * lanes;
+    for (int64_t m0 = (int64_t)blockIdx.x * lanes + pl; m0 < M; m0 += stride * UNR) {
+      float4 x[UNR], old[UNR];
+      float dy[UNR][4];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t m = m0 + u * stride;
+        x[u] = old[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dy[u][j] = 0.f;
+        if (m < M) {
+          x[u] = __ldg(reinterpret_cast<const float4*>(s.t.p + m * s.t.ldc + s.t.coff + ci));
+          if (e.accumulate)
+            old[u] = e.mode == 0 ? *reinterpret_cast<const float4*>(e.dx.p + m * e.dx.ldc + e.dx.coff + ci)
+                                 : *reinterpret_cast<const float4*>(e.du + m * c.Cin + ci);
+          const float* d = c.y.p + m * c.y.ldc + c.y.coff;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < c.Cout) dy[u][j] = __ldg(d + j);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const int64_t m = m0 + u * stride;
+        if (m >= M) break;
+        const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+        const float as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w}, cs[4] = {ctr.x, ctr.y, ctr.z, ctr.w};
+        float g[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float du = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) du = fmaf(dy[u][j], w[i][j], du);
+          if (s.relu && !(fmaf(as[i], xs[i], bs[i]) > 0.f)) du = 0.f;
+          p1[i] += du; p2[i] += du * (xs[i] - cs[i]);
+          g[i] = e.mode == 0 ? as[i] * du : du;
+        }
+        float4 o = make_float4(g[0] + old[u].x, g[1] + old[u].y, g[2] + old[u].z, g[3] + old[u].w);
+        if (e.mode == 0) *reinterpret_cast<float4*>(const_cast<float*>(e.dx.p) + m * e.dx.ldc + e.dx.coff + ci) = o;
+        else *reinterpret_cast<float4*>(e.du + m * c.Cin + ci) = o;
+      }
+    }
+  }
+  if (e.s1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { red[threadIdx.x * 8 + i] = p1[i]; red[threadIdx.x * 8 + 4 + i] = p2[i]; }
+    __syncthreads();
+    if (pl == 0) {
+      for (int l = 1; l < lanes; ++l)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { p1[i] += red[(l * nq + q) * 8 + i]; p2[i] += red[(l * nq + q) * 8 + 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { atomicAdd(e.s1 + ci + i, (double)p1[i]); atomicAdd(e.s2 + ci + i, (double)p2[i]); }
+    }
+  }
+}
+
+static bool small_n_shape(const hdn_conv* c) {
+  const hdn_src& s = c->src[0];
+  return c->kd * c->kh * c->kw == 1 && c->Cout <= 4 && c->Cin % 4 == 0 && c->Cin <= 256 && 256 % (c->Cin / 4) == 0 && c->nsrc == 1 &&
+         s.ud == 1 && s.uh == 1 && s.uw == 1 && c->sd == 1 && c->sh == 1 && c->sw == 1 && s.t.ldc % 4 == 0 && s.t.coff % 4 == 0 &&
+         (reinterpret_cast<uintptr_t>(s.t.p) & 15) == 0;
+}
+
 // out[c] += sum_m y[m][c]   (bias gradient)
 __global__ void __launch_bounds__(256) colsum_kernel(hdn_tensor y, int64_t M, int C, float* out,
                                                      int64_t rows_per_block) {
@@ -425,6 +575,16 @@ int hdn_conv_fprop_simt(const hdn_conv* c, cudaStream_t st) {
 }
 
 int hdn_conv_dgrad_simt(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_t st) {
+  if (small_n_shape(c) && epi[0].mode != 2 &&
+      (epi[0].mode == 1 || (epi[0].dx.ldc % 4 == 0 && epi[0].dx.coff % 4 == 0 && (reinterpret_cast<uintptr_t>(epi[0].dx.p) & 15) == 0))) {
+    const int64_t M = (int64_t)c->N * c->D * c->H * c->W;
+    const int nq = c->Cin / 4, lanes = 256 / nq;
+    int64_t blocks = hdn_cdiv(M, (int64_t)lanes * 4 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    conv_dgrad_small_n4<4><<<(unsigned)blocks, 256, 0, st>>>(*c, epi[0], M, nq);
+    HDN_CHECK_LAUNCH("conv_dgrad_small_n4");
+    return HDN_OK;
+  }
   for (int si = 0; si < c->nsrc; ++si) {
     if (epi[si].mode == 2) continue;
     const hdn_src& s = c->src[si];
@@ -446,6 +606,14 @@ int hdn_colsum(hdn_tensor y, int64_t M, int C, float* out, cudaStream_t st) {
 
 int hdn_conv_wgrad_simt(const hdn_conv* c, float* dw, cudaStream_t st) {
   const int64_t M = (int64_t)c->N * c->D * c->H * c->W;
+  if (small_n_shape(c)) {
+    const int nq = c->Cin / 4, lanes = 256 / nq;
+    int64_t blocks = hdn_cdiv(M, (int64_t)lanes * 4 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    conv_wgrad_small_n4<4><<<(unsigned)blocks, 256, 0, st>>>(*c, dw, M, nq);
+    HDN_CHECK_LAUNCH("conv_wgrad_small_n4");
+    return HDN_OK;
+  }
   if (c->kd * c->kh * c->kw == 1 && c->Cout <= 4 && c->Cin <= 256 && c->nsrc == 1 && c->src[0].ud == 1 && c->src[0].uh == 1 &&
       c->src[0].uw == 1 && c->sd == 1 && c->sh == 1 && c->sw == 1) {
     const int lanes = 256 / c->Cin;

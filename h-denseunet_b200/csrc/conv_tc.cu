@@ -90,6 +90,7 @@ struct TcParams {
   int fold;                   // bf16x3 with BN <= 128 (HDN_TC_X3FOLD, experiment): weight chunks laid out [head | tail] along N, the
                               //   accumulator is 2*BN columns wide, A_hi x [B_hi | B_lo] is ONE MMA (+ A_lo x B_hi): 2 MMAs per step
   int l2pf;                   // 1: raw patch copies carry the L2::256B prefetch hint (HDN_TC_L2PF, experiment)
+  int epi_pf;                 // 1: dgrad epilogue prefetches the next tile's stored values into L2 (HDN_TC_EPIPF, default 1)
   int epi4;                   // 1: dgrad epilogue in the quad form (16-byte stores / vector reductions; HDN_TC_EPI4, default 1)
   int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
@@ -215,7 +216,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint8_t* sRaw = sB + p.nsb * B_BYTES;
   int* tabs = reinterpret_cast<int*>(sRaw + (size_t)p.nraw * p.raw_bytes);
   float* sstat = reinterpret_cast<float*>(tabs + NTAB * p.tab_ints);        // [2 buffers][4][BN]
-  uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 15) & ~uintptr_t(15));
+  double* dstat = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 7) & ~uintptr_t(7));   // [4][BN] per-CTA sums
+  uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dstat + 4 * p.BN) + 15) & ~uintptr_t(15));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * EPI_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + MAXNSA;
@@ -708,11 +710,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #ifdef HDN_TC_TIMING
     long long te_wait = 0, te_work = 0;
 #endif
+    // Per-channel sums (batch statistics in fprop, S1 / S2 in dgrad) are accumulated per CTA in shared-memory doubles, each
+    // column owned by one epilogue thread, and reach global memory ONCE per CTA and column tile: a double atomic per tile
+    // and column from 148 CTAs onto the same few addresses serialises in L2 (16 384 tiles x 128 atomics for the 64-wide
+    // decoder tail) and throttled the whole pipeline.
+    for (int i = etid; i < 4 * p.BN; i += 128) dstat[i] = 0.0;
+    int flush_ntile = -1;
+    auto flush_stats = [&](int nt) {
+      if (p.mode == 0) {
+        for (int c = etid; c < p.BN; c += 128) {
+          const int col = nt * p.BN + c;
+          if (col < p.NC) { atomicAdd(p.stat_sum + col, dstat[c]); atomicAdd(p.stat_sq + col, dstat[p.BN + c]); }
+          dstat[c] = 0.0; dstat[p.BN + c] = 0.0;
+        }
+      } else {
+        for (int e = 0; e < p.nepi; ++e) {
+          const hdn_dgrad_epi& E = p.epi[e];
+          if (E.mode == 2 || E.s1 == nullptr) continue;
+          for (int c = etid; c < p.BN; c += 128) {
+            const int col = nt * p.BN + c;
+            const double s1 = dstat[(2 * e) * p.BN + c], s2 = dstat[(2 * e + 1) * p.BN + c];
+            if (col < p.NC) {
+              if (s1 != 0.0) atomicAdd(E.s1 + col, s1);
+              if (s2 != 0.0) atomicAdd(E.s2 + col, s2);
+            }
+            dstat[(2 * e) * p.BN + c] = 0.0; dstat[(2 * e + 1) * p.BN + c] = 0.0;
+          }
+        }
+      }
+    };
     for (long long w = blockIdx.x; w < p.total_work; w += gridDim.x, ++seq) {
       const TileC t = tile_decode(p, w);
       const int ab = seq & 1;
       float* st_ = sstat + ab * 4 * p.BN;
       const int n_tile = t.n_tile;
+      if (flush_ntile >= 0 && flush_ntile != n_tile) { flush_stats(flush_ntile); flush_ntile = -1; }
       bool rvalid;
       long long m;
       int oh = 0, ow = 0;
@@ -797,13 +829,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc::mbar_arrive(&acc_empty[ab]);                   // accumulator buffer may be overwritten
         if (do_stats) {
           bar_epilogue();
-          for (int c = etid; c < p.BN; c += 128) {
-            const int col = n_tile * p.BN + c;
-            if (col < p.NC) {
-              atomicAdd(p.stat_sum + col, (double)st_[c]);
-              atomicAdd(p.stat_sq + col, (double)st_[p.BN + c]);
-            }
-          }
+          for (int c = etid; c < p.BN; c += 128) { dstat[c] += (double)st_[c]; dstat[p.BN + c] += (double)st_[p.BN + c]; }
+          flush_ntile = n_tile;
         }
       } else if (p.scatter) {
         // dgrad of a stride-2 stem in space-to-depth form: column (rd,rh,rw,c) of s2d pixel (d0,oh,ow) is the
@@ -851,6 +878,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
         __syncwarp();
+        if (p.epi_pf) {
+          // The stored values this epilogue reads were written a whole forward pass ago: they come from DRAM, and the few
+          // 16-byte loads a lane keeps in flight make the epilogue latency-bound.  Pull the NEXT tile's rows into L2 now
+          // (one row per thread, a prefetch per 128-byte line): by the time that tile's accumulator is ready they are L2 hits.
+          const long long wn = w + gridDim.x;
+          if (wn < p.total_work) {
+            const TileC tn = tile_decode(p, wn);
+            const int ncb = min(p.BN, p.NC - tn.n_tile * p.BN) * 4;            // bytes of this column tile per row
+            for (int e = 0; e < p.nepi; ++e) {
+              if (p.epi[e].mode == 2) continue;
+              const hdn_src& S = p.esrc[e];
+              long long ms;
+              bool wr_ = true;
+              if (p.flat) { ms = tn.m0 + row; wr_ = ms < p.M; }
+              else {
+                const int ohn = tn.h0 + hr, own = tn.w0 + wr;
+                wr_ = ohn < p.H && own < p.W && !(S.uw == 2 && (wr & 1)) && !(S.uh == 2 && (hr & 1));
+                const int sd = (S.ud == 2) ? (tn.d0 >> 1) : tn.d0, sh = (S.uh == 2) ? (ohn >> 1) : ohn, sw = (S.uw == 2) ? (own >> 1) : own;
+                ms = (((long long)tn.n_img * S.D + sd) * S.H + sh) * S.W + sw;
+              }
+              if (wr_) {
+                const char* px = reinterpret_cast<const char*>(S.t.p + ms * (long long)S.t.ldc + S.t.coff + tn.n_tile * p.BN);
+                for (int o = 0; o < ncb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+              }
+            }
+          }
+        }
         for (int cb = 0; cb < p.BN; cb += 32) {
           const int ncols = min(32, p.BN - cb);
           float v2[16];
@@ -996,20 +1050,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const hdn_dgrad_epi& E = p.epi[e];
             if (E.mode == 2 || E.s1 == nullptr) continue;
             for (int c = etid; c < p.BN; c += 128) {
-              const int col = n_tile * p.BN + c;
-              if (col < p.NC) {
-                const float s1 = st_[(2 * e) * p.BN + c], s2 = st_[(2 * e + 1) * p.BN + c];
-                if (s1 != 0.f) atomicAdd(E.s1 + col, (double)s1);
-                if (s2 != 0.f) atomicAdd(E.s2 + col, (double)s2);
-              }
+              dstat[(2 * e) * p.BN + c] += (double)st_[(2 * e) * p.BN + c];
+              dstat[(2 * e + 1) * p.BN + c] += (double)st_[(2 * e + 1) * p.BN + c];
             }
           }
+          flush_ntile = n_tile;
         }
       }
 #ifdef HDN_TC_TIMING
       te_work += clock64() - te0;
 #endif
     }
+    if (flush_ntile >= 0) flush_stats(flush_ntile);
 #ifdef HDN_TC_TIMING
     if (blockIdx.x == 0 && etid == 0) printf("[epi] tiles %d  wait %lld  work %lld (cycles/tile)\n", seq, te_wait / max(seq, 1), te_work / max(seq, 1));
 #endif
@@ -1165,13 +1217,14 @@ int hdn_tc_x3fold() {
 int hdn_tc_tail16() { return 0; }
 
 // HDN_TC_TMA: which fprop / dgrad launches take the TMA mode (bf16 operand pre-pass + tile loads instead of the SIMT
-// producers): 0 none, 1 the 1x3x3 / 3x3x3 layers (default), 2 also the 1x1x1 layers.  Stems keep their own producer.
+// producers): 0 none, 1 the 1x3x3 / 3x3x3 layers, 2 also the 1x1x1 layers (default: measured 656 vs 664 ms per headline
+// step, profiles/r02g_*).  Stems keep their own producer.
 static int g_tc_tma = -1;
 int hdn_tc_tma() {
   if (g_tc_tma < 0) {
     const char* e = getenv("HDN_TC_TMA");
-    g_tc_tma = e ? atoi(e) : 1;
-    if (g_tc_tma < 0 || g_tc_tma > 2) g_tc_tma = 1;
+    g_tc_tma = e ? atoi(e) : 2;
+    if (g_tc_tma < 0 || g_tc_tma > 2) g_tc_tma = 2;
   }
   return g_tc_tma;
 }
@@ -1307,7 +1360,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   if (pl.tma) {
     // no raw ring, no geometry tables: the A ring gets up to 4 stages next to >= taps_hw (<= 12) weight blocks
     pl.tab_ints = 0; pl.raw_bytes = 0;
-    const size_t fix = 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128;
+    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 4ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128;
     const int want_b = g.kh * g.kw < 4 ? 4 : (g.kh * g.kw > 12 ? 12 : g.kh * g.kw);
     int nsa = 4;
     while (nsa > 2 && (long long)(fix + nsa * a_bytes + (size_t)want_b * b_bytes) > budget) --nsa;
@@ -1320,7 +1373,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
     pl.op_elems = (long long)c->N * c->D * c->H * c->W * g.K;
     return pl;
   }
-  const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 16 + 4ull * EPI_BYTES +
+  const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 4ull * EPI_BYTES +
                       (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16;
   // raw fp32 ring: 3 stages when they fit next to two weight blocks, else 2; the weight ring takes what is left:
   // every tile streams ALL its weight blocks from L2, so the bytes in flight there set the pace of narrow layers
@@ -1416,6 +1469,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.tail16 = tail16;
   p.fastx = hdn_tc_fastx();
   { static int v = -1; if (v < 0) { const char* e = getenv("HDN_TC_EPI4"); v = (e && atoi(e) == 0) ? 0 : 1; } p.epi4 = v; }
+  { static int v = -1; if (v < 0) { const char* e = getenv("HDN_TC_EPIPF"); v = (e && atoi(e) == 0) ? 0 : 1; } p.epi_pf = v; }
   p.l2pf = hdn_tc_l2pf();
   p.fold = pl.fold;
   if (mode == 0) {

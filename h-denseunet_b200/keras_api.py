@@ -10,6 +10,7 @@
                                                        the HDF5 reader is a SURVEY 8f 'next' row)
   SGD(lr, momentum, nesterov)                          optimizers.py:130-186
 """
+import contextlib
 import os
 import time
 
@@ -150,7 +151,13 @@ class Model(object):
         st = self._staging.get(key)
         cuda = dev.type == "cuda"
         if st is None:
-            st = (torch.empty(x.shape, dtype=tdt, pin_memory=cuda), torch.empty(x.shape, dtype=tdt, device=dev))
+            if cuda and self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            # the device staging buffer belongs to the COPY stream's allocator pool: a block taken from the compute stream's
+            # pool may still be read by a kernel queued there (a freed temporary), and the H2D copy would overwrite it
+            with (torch.cuda.stream(self._copy_stream) if cuda else contextlib.nullcontext()):
+                dbuf = torch.empty(x.shape, dtype=tdt, device=dev)
+            st = (torch.empty(x.shape, dtype=tdt, pin_memory=cuda), dbuf)
             self._staging[key] = st
         ev = self._staging_ev.get(key)
         if ev is not None:

@@ -48,8 +48,8 @@ def test_every_convolution_has_a_valid_plan(plan_rows, prec):
             nsplit = 2 if prec == 2 else 1
             wbytes = tiles * kb * bn * ck * 2 * nsplit
             assert ws > 0 and (ws % (bn * ck * 2 * nsplit) == 0 or ws > wbytes), what
-            if P == 180:
-                # TMA mode (default for the 1x3x3 / 3x3x3 layers): packed weights + the pre-packed bf16 head (+ tail) operand
+            if P in (180, 128) and not s2d:
+                # TMA mode (default for every stride-1 layer): packed weights + the pre-packed bf16 head (+ tail) operand
                 k = k_or_bne
                 opb = (M * k * 2 + 255) // 256 * 256
                 assert ws >= opb * nsplit and (ws - opb * nsplit) % 256 == 0, what
@@ -69,9 +69,9 @@ def test_every_convolution_has_a_valid_plan(plan_rows, prec):
 
 def test_bf16x3_workspace_is_twice_the_bf16_one_per_channel_block(plan_rows):
     """bf16x3 packs a head and a tail block per (column tile, K block, tap): same bytes per covered channel x2."""
-    # (layers in the SIMT-producer form: stems and 1x1x1; the TMA-mode layers add their operand tensors to the scratch)
-    a = {(n, ps): (o, ws) for n, ps, o, ws, _ in plan_rows[1] if o is not None and ps < 2 and (o[8] or o[11])}
-    b = {(n, ps): (o, ws) for n, ps, o, ws, _ in plan_rows[2] if o is not None and ps < 2 and (o[8] or o[11])}
+    # (layers in the SIMT-producer form: the stems; the TMA-mode layers add their operand tensors to the scratch)
+    a = {(n, ps): (o, ws) for n, ps, o, ws, _ in plan_rows[1] if o is not None and ps < 2 and (o[11] or o[9] == 209)}
+    b = {(n, ps): (o, ws) for n, ps, o, ws, _ in plan_rows[2] if o is not None and ps < 2 and (o[11] or o[9] == 209)}
     assert a.keys() == b.keys()
     for key in a:
         (o1, w1), (o2, w2) = a[key], b[key]

@@ -27,12 +27,26 @@ CASES = {
 }
 
 
+def headline(kw):
+    """The same layer at the headline batch: 2 slabs of 48 slices (3-D layers: N=2, D=48; 2-D layers: N=96)."""
+    kw = dict(kw)
+    if kw["D"] > 1:
+        kw["N"], kw["D"] = 2, 48
+    else:
+        kw["N"] = 96
+    return kw
+
+
 def main():
     name, which = sys.argv[1], sys.argv[2]
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     prec = int(sys.argv[4]) if len(sys.argv) > 4 else 1
     dev = torch.device("cuda:0")
-    c = Case(dev, tc=prec, **CASES[name])
+    kw = CASES[name]
+    full = os.environ.get("HDN_PROF_FULL", "0") not in ("", "0")
+    if full:
+        kw = headline(kw)
+    c = Case(dev, tc=prec, device_fill=full, **kw)
     op, d, net = c.op, c.op.desc, c.net
     flops = 2.0 * d.out.M * d.Cin * d.Cout * d.k[0] * d.k[1] * d.k[2]
     if which == "fprop":

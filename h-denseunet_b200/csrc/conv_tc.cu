@@ -62,7 +62,6 @@ constexpr int NSB_MAX = 16;   // weight-block ring depth upper bound
 constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs at most 3 stages ahead of the transform)
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
-constexpr int RB = 16;        // dgrad epilogue, scalar fallback form: rows fetched ahead per lane
 constexpr int MAXC0 = 14;     // copies per producer thread and stage, source 0 (4-tap stems' dgrad: 19x11 px x 16 quads / 256 threads)
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 
@@ -91,7 +90,6 @@ struct TcParams {
                               //   accumulator is 2*BN columns wide, A_hi x [B_hi | B_lo] is ONE MMA (+ A_lo x B_hi): 2 MMAs per step
   int l2pf;                   // 1: raw patch copies carry the L2::256B prefetch hint (HDN_TC_L2PF, experiment)
   int epi_pf;                 // 1: dgrad epilogue prefetches the next tile's stored values into L2 (HDN_TC_EPIPF, default 1)
-  int epi4;                   // 1: dgrad epilogue in the quad form (16-byte stores / vector reductions; HDN_TC_EPI4, default 1)
   int fastx;                  // 1: warp-per-chunk operand transform (tc::xform_chunk) where the prologue shape allows
   int split;                  // 1: bf16x3 -- stage = 32 channels, A chunks [0,4) head / [4,8) tail, weight block = head | tail
   int tail16;                 // 1: the tails of both operands are IEEE half instead of bfloat16 (HDN_TC_TAIL16; ~19 instead of ~16 significant bits)
@@ -901,6 +899,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (wr_) {
                 const char* px = reinterpret_cast<const char*>(S.t.p + ms * (long long)S.t.ldc + S.t.coff + tn.n_tile * p.BN);
                 for (int o = 0; o < ncb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+                const hdn_dgrad_epi& E = p.epi[e];
+                if (E.accumulate && S.ud != 2) {                     // the old gradient values of the read-modify-write form
+                  const char* pg = E.mode == 0 ? reinterpret_cast<const char*>(E.dx.p + ms * (long long)E.dx.ldc + E.dx.coff + tn.n_tile * p.BN)
+                                               : reinterpret_cast<const char*>(E.du + ms * (long long)p.NC + tn.n_tile * p.BN);
+                  for (int o = 0; o < ncb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + o));
+                }
               }
             }
           }
@@ -917,13 +921,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) tT[lane * 33 + 16 + i] = rvalid ? v2[i] : 0.f;
           }
           __syncwarp();
-          const int col = n_tile * p.BN + cb + lane;
-          const bool cok = lane < ncols && col < p.NC;
           for (int e = 0; e < p.nepi; ++e) {
             const hdn_dgrad_epi& E = p.epi[e];
             if (E.mode == 2) continue;
             const hdn_src& S = p.esrc[e];
-            if (p.epi4) {
+            {
               // Quad form: lane = (row sub-index, channel quad).  A lane owns 4 consecutive channels of rows 4*it + rsub:
               // the stored values arrive as 16-byte loads, the gradient leaves as ONE 16-byte store or vector reduction
               // per row (red.global.add.v4.f32) instead of four 4-byte REDs -- the dense blocks' 1x1 data gradients issue
@@ -945,17 +947,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const long long* rd = rod + e * 32;
               const unsigned wm = wmask[e];
               float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-              // two batches of 4 rows: the 4 stored-value loads of a batch are in flight together
-              for (int it0 = 0; it0 < 8; it0 += 4) {
-                float4 xs[4];
+              // An accumulating write that no other CTA touches (everything but a depth-up-sampled source) is a plain
+              // load + add + store: the reduction unit retires ~1 element per cycle per SM, which bounded the dense blocks'
+              // 1x1 data gradients (measured 63k cycles of epilogue per 128 x 240 tile, profiles/r02j_role_timing.txt);
+              // the old values are fetched in the same batch as the stored activations.
+              const bool rmw = acc && !atom;
+              for (int it0 = 0; it0 < 8; it0 += 2) {             // batches of 2 rows: 2 stored values + 2 old gradients in flight
+                float4 xs[2], os[2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                   const int rr = 4 * (it0 + k) + rsub;
                   xs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  if (qok && ((wm >> rr) & 1u)) xs[k] = ldg4(xb + rx[rr] + col4);
+                  os[k] = xs[k];
+                  if (qok && ((wm >> rr) & 1u)) {
+                    xs[k] = ldg4(xb + rx[rr] + col4);
+                    if (rmw) os[k] = *reinterpret_cast<const float4*>(db + rd[rr] + col4);
+                  }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 2; ++k) {
                   const int rr = 4 * (it0 + k) + rsub;
                   if (!(qok && ((wm >> rr) & 1u))) continue;
                   const float* tp = tT + rr * 33 + 4 * cq;
@@ -976,10 +986,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   s2.x += dz.x * (x.x - c4.x); s2.y += dz.y * (x.y - c4.y); s2.z += dz.z * (x.z - c4.z); s2.w += dz.w * (x.w - c4.w);
                   float* q = db + rd[rr] + col4;
                   const float4 g = make_float4(ga.x * dz.x, ga.y * dz.y, ga.z * dz.z, ga.w * dz.w);
-                  if (atom | acc)
+                  if (atom)
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
                   else
-                    *reinterpret_cast<float4*>(q) = g;
+                    *reinterpret_cast<float4*>(q) = make_float4(g.x + os[k].x, g.y + os[k].y, g.z + os[k].z, g.w + os[k].w);
                 }
               }
               if (E.s1) {                                                // (warp-uniform) fold the 4 row sub-indices of a quad
@@ -997,46 +1007,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   atomicAdd(p2, s2.x); atomicAdd(p2 + 1, s2.y); atomicAdd(p2 + 2, s2.z); atomicAdd(p2 + 3, s2.w);
                 }
               }
-            } else if (cok) {
-              const float a = S.pa ? __ldg(S.pa + col) : 1.f, b = S.pb ? __ldg(S.pb + col) : 0.f;
-              const float ctr = (E.s1 && E.center) ? __ldg(E.center + col) : 0.f;
-              const bool up_w = S.uw == 2, up_h = S.uh == 2, atom = S.ud == 2, acc = E.accumulate != 0, relu = S.relu != 0;
-              const float* xb = S.t.p;
-              float* db = E.mode == 0 ? const_cast<float*>(E.dx.p) : E.du;
-              const float ga = E.mode == 0 ? a : 1.f;
-              const long long* rx = rox + e * 32;
-              const long long* rd = rod + e * 32;
-              const unsigned wm = wmask[e];
-              float s1 = 0.f, s2 = 0.f;
-              // rows in batches of RB: all stored values of a batch are requested before any is used; an accumulating
-              // write is a fire-and-forget reduction (RED.ADD executes in L2: no read latency on the SM side)
-              for (int r0 = 0; r0 < 32; r0 += RB) {
-                const unsigned bm = (RB == 32) ? wm : ((wm >> r0) & ((1u << (RB & 31)) - 1u));
-                if (!bm) continue;                               // warp-uniform: no writer row in this batch
-                float xs[RB];
-#pragma unroll
-                for (int k = 0; k < RB; ++k) {
-                  xs[k] = 0.f;
-                  if ((wm >> (r0 + k)) & 1u) xs[k] = __ldg(xb + rx[r0 + k] + col);
-                }
-#pragma unroll
-                for (int k = 0; k < RB; ++k) {
-                  const int rr = r0 + k;
-                  if (!((wm >> rr) & 1u)) continue;            // warp-uniform
-                  float dz = tT[rr * 33 + lane];
-                  if (up_w) dz += tT[(rr ^ 1) * 33 + lane];
-                  if (up_h) { dz += tT[(rr ^ 8) * 33 + lane]; if (up_w) dz += tT[(rr ^ 9) * 33 + lane]; }
-                  const float x = xs[k];
-                  float du = dz;
-                  if (relu && !(fmaf(a, x, b) > 0.f)) du = 0.f;
-                  s1 += du; s2 += du * (x - ctr);
-                  float* q = db + rd[rr] + col;
-                  const float g = ga * du;
-                  if (atom | acc) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(g) : "memory");
-                  else *q = g;
-                }
-              }
-              if (E.s1) { atomicAdd(&st_[(2 * e) * p.BN + cb + lane], s1); atomicAdd(&st_[(2 * e + 1) * p.BN + cb + lane], s2); }
             }
           }
           __syncwarp();
@@ -1468,7 +1438,6 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.split = nsplit == 2 ? 1 : 0;
   p.tail16 = tail16;
   p.fastx = hdn_tc_fastx();
-  { static int v = -1; if (v < 0) { const char* e = getenv("HDN_TC_EPI4"); v = (e && atoi(e) == 0) ? 0 : 1; } p.epi4 = v; }
   { static int v = -1; if (v < 0) { const char* e = getenv("HDN_TC_EPIPF"); v = (e && atoi(e) == 0) ? 0 : 1; } p.epi_pf = v; }
   p.l2pf = hdn_tc_l2pf();
   p.fold = pl.fold;

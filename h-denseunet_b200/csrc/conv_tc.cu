@@ -30,8 +30,10 @@
 #include "tc_common.cuh"
 
 // shared with the tc2 weight gradient (conv_tc2_wgrad.cu): bf16 operand pre-pass and tensor maps over its output
-int hdn_tc2_make_map(CUtensorMap* tm, const void* base, int flat, long long M, int N, int D, int H, int W, int C, int bc, int bw, int bh);
-int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+int hdn_tc2_make_map(CUtensorMap* tm, const void* base, int flat, long long M, int N, int D, int H, int W, int C, int bc, int bw, int bh,
+                     int swizzle128);
+int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st,
+                 int interleave);
 
 // -DHDN_TC_TIMING: per-role wait/work cycle counters of CTA 0, printed at kernel end (development aid)
 #ifdef HDN_TC_TIMING
@@ -70,6 +72,9 @@ struct TcParams {
   int tma;                    // 1: the A operand was pre-packed to bf16 by hdn_tc2_pack and is staged by TMA tile loads (one box
                               //    {8 channels, PW, PH} per chunk plane; out-of-bounds = the zero padding); no SIMT producers
   int nsa;                    // A-operand stages in the ring (2 in the SIMT-producer form)
+  int sw;                     // TMA mode, SWIZZLE_128B form (HDN_TC_SW128): a stage is ONE box {64, PW, PH} of 128-byte pixel rows
+                              //   ([head 32 | tail 32] channels in bf16x3), weights packed as swizzled 128-byte rows; K-major SW128
+                              //   descriptors with SBO = PW*128 and sub-row K offsets
   int N, D, H, W;             // GEMM row grid = conv output grid = virtual (up-sampled) input grid
   int kd, kh, kw;
   int K, NC;                  // contraction channels, output columns
@@ -203,9 +208,11 @@ __device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q,
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // the 128-byte swizzle is a function of the shared-memory address bits 4-9: stages start on 1024-byte boundaries
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t A_BYTES = 8u * p.Ppad * 16u;
+  const uint32_t A_BYTES = p.sw ? (((uint32_t)p.P * 128u + 1023u) & ~1023u) : 8u * p.Ppad * 16u;
   const uint32_t B_HALF = (uint32_t)p.BN * (uint32_t)p.CK * 2u;          // one bf16 weight block
   const uint32_t B_BYTES = p.split ? 2u * B_HALF : B_HALF;                 // bf16x3: head block | tail block
   const int nsa = p.nsa;
@@ -304,6 +311,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t box_bytes = (uint32_t)p.P * 16u;
         while (!tr.done) {
           tc::mbar_wait(&a_empty[sa], pha ^ 1);
+          if (p.sw) {
+            if (tc::elect_one_sync()) {
+              uint8_t* dst = sA + sa * A_BYTES;
+              tc::mbar_arrive_expect_tx(&a_full[sa], (uint32_t)p.P * 128u);
+              if (p.flat) tc::tma_load_2d(dst, &p.tmHi, &a_full[sa], tr.kb * 64, (int)tr.t.m0);
+              else tc::tma_load_5d(dst, &p.tmHi, &a_full[sa], tr.kb * 64, tr.t.w0 - p.pw_lo, tr.t.h0 - p.ph_lo, tr.t.d0 - p.pd_lo + tr.dz, tr.t.n_img);
+            }
+          } else
           if (tc::elect_one_sync()) {
             uint8_t* dst = sA + sa * A_BYTES;
             const int c0 = tr.kb * p.CK;
@@ -605,9 +620,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t pha = 0, phb = 0;
       int cur_seq = -1;
       uint32_t acc = 0, tmem_d = tmem_base;
-      const uint64_t adesc_hi = tc::make_smem_desc(0, lbo_a, sbo_a), bdesc_hi = tc::make_smem_desc(0, lbo_b, sbo_b);
-      const uint64_t kstep_a = (uint64_t)((2u * lbo_a) >> 4), kstep_b = (uint64_t)((2u * lbo_b) >> 4);
-      const uint64_t tail_a = (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_a) >> 4), tail_b = (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_b) >> 4);
+      // SWIZZLE_128B form: rows (pixels / output channels) are 128 bytes, 8-row groups SBO apart, K advances inside the row
+      const uint64_t sw_bit = (uint64_t)2 << 61;
+      const uint64_t adesc_hi = p.sw ? (tc::make_smem_desc(0, 16u, (uint32_t)p.PW * 128u) | sw_bit) : tc::make_smem_desc(0, lbo_a, sbo_a);
+      const uint64_t bdesc_hi = p.sw ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, lbo_b, sbo_b);
+      const uint64_t kstep_a = p.sw ? 2u : (uint64_t)((2u * lbo_a) >> 4), kstep_b = p.sw ? 2u : (uint64_t)((2u * lbo_b) >> 4);
+      const uint64_t tail_a = p.sw ? 4u : (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_a) >> 4);
+      const uint64_t tail_b = p.sw ? 4u : (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_b) >> 4);
+      const uint32_t pixu = p.sw ? 8u : 1u;                  // 16-byte units per patch pixel
       // folded bf16x3: chunk stride of the [head | tail] weight block is 2*BN rows; N = 2*BN for A_hi, N = BN for A_lo
       const uint32_t idesc_f2 = tc::make_idesc_bf16(128, 2 * p.BN, 0, 0);
       const uint64_t bdesc_hi_f = tc::make_smem_desc(0, 2u * lbo_b, sbo_b), kstep_b_f = (uint64_t)((4u * lbo_b) >> 4);
@@ -638,7 +658,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           tc::mbar_wait(&b_full[sb], phb);
           tc::tc_fence_after();
           TT_ADD(t_bfull);
-          const uint64_t ad = a_desc0 + tap_units;
+          const uint64_t ad = a_desc0 + (uint64_t)(tap_units * pixu);
           const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
           if (tc::elect_one_sync()) {
           if (!p.split) {
@@ -1098,6 +1118,47 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
   }
 }
 
+// SWIZZLE_128B form of the packed weights: out[n_tile][kb][tap][n < BN][64 k] as 128-byte rows whose 16-byte chunks are
+// XOR-swizzled with the row index (chunk c of row n sits at (c ^ (n & 7))), the layout a K-major SWIZZLE_128B descriptor
+// reads when the block starts on a 1024-byte boundary.  bf16x3: k = [head of channels kb*32 .. +32 | tail of the same].
+__global__ void __launch_bounds__(256) pack_weights_sw_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout,
+                                                              int kd, int kh, int kw, int BN, int KB, int role, int split, long long total16) {
+  const int T = kd * kh * kw;
+  const int K = role == 0 ? Cin : Cout, NC = role == 0 ? Cout : Cin;
+  for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total16; idx += (long long)gridDim.x * 256) {
+    long long t = idx;
+    const int c = (int)(t & 7); t >>= 3;
+    const int n = (int)(t % BN); t /= BN;
+    const int tap = (int)(t % T); t /= T;
+    const int kb = (int)(t % KB); t /= KB;
+    const int nt = (int)t;
+    const int part = split ? (c >> 2) : 0;
+    const int k0 = split ? kb * 32 + (c & 3) * 8 : kb * 64 + c * 8;
+    const int col = nt * BN + n;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (col < NC && k0 < K) {
+      if (role == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(w + ((long long)tap * Cin + k0 + e) * Cout + col);
+      } else {
+        const float* src = w + ((long long)(T - 1 - tap) * Cin + col) * Cout + k0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e);
+      }
+    }
+    if (part) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16_rn(v[e]));
+    }
+    uint4 o;
+    o.x = tc::pack_bf16x2(v[0], v[1]); o.y = tc::pack_bf16x2(v[2], v[3]);
+    o.z = tc::pack_bf16x2(v[4], v[5]); o.w = tc::pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[(idx & ~7ll) + (long long)(c ^ (n & 7))] = o;
+  }
+}
+
 // Stride-2 stems in space-to-depth form (7-tap kernel, pad 3, stride 2 == 4-tap kernel over the s2d input):
 // s2d tap tq (0..3) and sub-position r (0/1) read original tap t = 2*tq + r - 1 (t = -1 does not exist -> 0).
 //   role 0 (fprop): B[n = co][k = (rd,rh,rw,c)] = w[t(tq,r)][c][co]
@@ -1200,6 +1261,18 @@ int hdn_tc_tma() {
 }
 void hdn_tc_tma_set(int v) { g_tc_tma = v < 0 ? 0 : (v > 2 ? 2 : v); }
 
+// HDN_TC_SW128=0|1: TMA mode with SWIZZLE_128B operand rows (one tile load per stage, swizzled weight rows) instead of the
+// 16-byte chunk planes; also hdn_set_switch()
+static int g_tc_sw128 = -1;
+int hdn_tc_sw128() {
+  if (g_tc_sw128 < 0) {
+    const char* e = getenv("HDN_TC_SW128");
+    g_tc_sw128 = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_tc_sw128;
+}
+void hdn_tc_sw128_set(int v) { g_tc_sw128 = v ? 1 : 0; }
+
 // HDN_TC_L2PF=1: experiment switch, see TcParams::l2pf (default 0)
 int hdn_tc_l2pf() {
   static int v = -1;
@@ -1213,7 +1286,7 @@ int hdn_tc_l2pf() {
 namespace {
 
 struct TcPlan {
-  int tma, nsa;                     // TMA mode (pre-packed bf16 operand), A-ring depth
+  int tma, nsa, sw;                 // TMA mode (pre-packed bf16 operand), A-ring depth, SWIZZLE_128B form
   long long op_elems;               // bf16 elements of one pre-packed operand tensor (head; the tail doubles it)
   int fold;
   int BN, n_tiles, KB, CK, nsb, nraw, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
@@ -1290,6 +1363,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   pl.tma = (!g.s2d && !g.scatter && (long long)c->N * c->D * c->H * c->W < (1ll << 31) &&
             (tma_level >= 2 || (tma_level == 1 && !g.flat))) ? 1 : 0;
   pl.nsa = NSA;
+  pl.sw = (pl.tma && hdn_tc_sw128()) ? 1 : 0;
   const int nsplit = c->precision == 2 ? 2 : 1;           // bf16x3: head + tail of every operand
   pl.n_tiles = (g.NC + 255) / 256 + extra_tiles;
   int bn = (g.NC + pl.n_tiles - 1) / pl.n_tiles;
@@ -1320,7 +1394,8 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   for (int s = 0; s < 2; ++s) { pl.ab_off[s] = off; off += s < nsrc ? 2 * pl.CK * 4 : 0; }
   pl.raw_bytes = (off + 127) / 128 * 128;
   pl.tab_ints = toff;
-  const size_t a_bytes = 8ull * pl.Ppad * 16, b_bytes = (size_t)pl.BN * pl.CK * 2 * nsplit;
+  const size_t a_bytes = pl.sw ? ((size_t)pl.P * 128 + 1023) / 1024 * 1024 : 8ull * pl.Ppad * 16;
+  const size_t b_bytes = (size_t)pl.BN * pl.CK * 2 * nsplit;
   pl.fold = (kFold && nsplit == 2 && hdn_tc_x3fold() && pl.BN <= 128) ? 1 : 0;
   int cols = 32;
   while (cols < 2 * pl.BN * (pl.fold ? 2 : 1)) cols *= 2;  // two accumulator buffers
@@ -1330,7 +1405,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   if (pl.tma) {
     // no raw ring, no geometry tables: the A ring gets up to 4 stages next to >= taps_hw (<= 12) weight blocks
     pl.tab_ints = 0; pl.raw_bytes = 0;
-    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 4ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128;
+    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 4ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128 + 1024;
     const int want_b = g.kh * g.kw < 4 ? 4 : (g.kh * g.kw > 12 ? 12 : g.kh * g.kw);
     int nsa = 4;
     while (nsa > 2 && (long long)(fix + nsa * a_bytes + (size_t)want_b * b_bytes) > budget) --nsa;
@@ -1340,11 +1415,12 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
     pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
     pl.nraw = (room >= 2 * (long long)b_bytes) ? nsa : 0;      // reported in the plan's ring-depth slot; 0 = does not fit (narrower tile)
     pl.smem = fix + (size_t)nsa * a_bytes + (size_t)pl.nsb * b_bytes;
-    pl.op_elems = (long long)c->N * c->D * c->H * c->W * g.K;
+    // one operand tensor: K channels per pixel, or -- SWIZZLE_128B form of bf16x3 -- [head 32 | tail 32] per 32-channel group
+    pl.op_elems = (long long)c->N * c->D * c->H * c->W * ((pl.sw && nsplit == 2) ? (g.K + 31) / 32 * 32 : g.K);
     return pl;
   }
   const size_t base = NSA * a_bytes + (size_t)NTAB * pl.tab_ints * 4 + 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 4ull * EPI_BYTES +
-                      (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16;
+                      (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 1024;
   // raw fp32 ring: 3 stages when they fit next to two weight blocks, else 2; the weight ring takes what is left:
   // every tile streams ALL its weight blocks from L2, so the bytes in flight there set the pace of narrow layers
   pl.nraw = 0;
@@ -1392,7 +1468,9 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   {
     long long total = pl.ws_elems / 8;
     unsigned gr = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
-    if (g.s2d || g.scatter)
+    if (pl.sw)
+      pack_weights_sw_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, mode, nsplit == 2 ? 1 : 0, total);
+    else if (g.s2d || g.scatter)
       pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
     else
       pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
@@ -1400,24 +1478,32 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   }
   TcParams p;
   memset(&p, 0, sizeof(p));
-  p.tma = pl.tma; p.nsa = pl.nsa;
+  p.tma = pl.tma; p.nsa = pl.nsa; p.sw = pl.sw;
   if (pl.tma) {
     // operand pre-pass (once per launch): fprop -- max(a*x+b, 0) (+ second source) on the virtual grid; dgrad -- dY
     __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(c->ws) + w_bytes);
     __nv_bfloat16* lo = nsplit == 2 ? reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(c->ws) + w_bytes + op_bytes) : nullptr;
     int rc;
-    if (mode == 0) rc = hdn_tc2_pack(c->src, c->nsrc, c->N, c->D, c->H, c->W, c->Cin, hi, lo, st);
+    const int il = (pl.sw && nsplit == 2) ? 1 : 0;            // interleaved [head | tail] rows in ONE tensor
+    if (il) lo = nullptr;
+    if (mode == 0) rc = hdn_tc2_pack(c->src, c->nsrc, c->N, c->D, c->H, c->W, c->Cin, hi, lo, st, il);
     else {
       hdn_src dys;
       memset(&dys, 0, sizeof(dys));
       dys.t = c->y; dys.D = c->D; dys.H = c->H; dys.W = c->W; dys.ud = dys.uh = dys.uw = 1;
-      rc = hdn_tc2_pack(&dys, 1, c->N, c->D, c->H, c->W, c->Cout, hi, lo, st);
+      rc = hdn_tc2_pack(&dys, 1, c->N, c->D, c->H, c->W, c->Cout, hi, lo, st, il);
     }
     if (rc) return rc;
     const long long Mv = (long long)c->N * c->D * c->H * c->W;
-    rc = hdn_tc2_make_map(&p.tmHi, hi, pl.flat, Mv, c->N, c->D, c->H, c->W, g.K, 8, pl.PW, pl.PH);
-    if (rc) return rc;
-    if (lo) { rc = hdn_tc2_make_map(&p.tmLo, lo, pl.flat, Mv, c->N, c->D, c->H, c->W, g.K, 8, pl.PW, pl.PH); if (rc) return rc; }
+    if (pl.sw) {
+      const int C2 = il ? (g.K + 31) / 32 * 64 : g.K;
+      rc = hdn_tc2_make_map(&p.tmHi, hi, pl.flat, Mv, c->N, c->D, c->H, c->W, C2, 64, pl.PW, pl.PH, 1);
+      if (rc) return rc;
+    } else {
+      rc = hdn_tc2_make_map(&p.tmHi, hi, pl.flat, Mv, c->N, c->D, c->H, c->W, g.K, 8, pl.PW, pl.PH, 0);
+      if (rc) return rc;
+      if (lo) { rc = hdn_tc2_make_map(&p.tmLo, lo, pl.flat, Mv, c->N, c->D, c->H, c->W, g.K, 8, pl.PW, pl.PH, 0); if (rc) return rc; }
+    }
   }
   p.N = c->N; p.D = c->D; p.H = c->H; p.W = c->W;
   p.kd = g.kd; p.kh = g.kh; p.kw = g.kw;
@@ -1517,6 +1603,7 @@ long long hdn_tc_workspace_bytes(const hdn_conv* c, int pass) {
   const long long w_bytes = (pl.ws_elems * 2 + 255) / 256 * 256;
   if (!pl.tma) return pl.ws_elems * 2;
   return w_bytes + (pl.op_elems * 2 + 255) / 256 * 256 * (c->precision == 2 ? 2 : 1);      // packed weights + bf16 head (+ tail) operand
+                                                                                        // (SWIZZLE_128B form: one interleaved tensor of the same size)
 }
 
 // launch plan of the fprop / dgrad kernel for this descriptor (host arithmetic only; see hdn_conv_tc_plan in hdn.h)

@@ -275,11 +275,13 @@ struct PackParams {
   hdn_src src[2];
   __nv_bfloat16* out;
   __nv_bfloat16* out_lo;              // optional: bf16 tail x - bf16(x) (the second operand term of bf16x3)
-  long long total;                    // pixels * (C / 8)
+  int interleave;                     // 1: ONE output tensor of 2*ceil32(C) channels per pixel, [head 32 | tail 32] per 32-channel group
+                                      //    (a 128-byte row = one K stage of the SWIZZLE_128B form); channels >= C are written as zeros
+  long long total;                    // pixels * (C / 8)   (interleave: pixels * (ceil32(C) / 8))
 };
 
 __global__ void __launch_bounds__(256) act_pack_bf16_kernel(const __grid_constant__ PackParams p) {
-  const int nch = p.C >> 3;
+  const int nch = p.interleave ? ((p.C + 31) / 32 * 4) : (p.C >> 3);
   for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < p.total; idx += (long long)gridDim.x * 256) {
     const long long m = idx / nch;
     const int c = (int)(idx - m * nch) * 8;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(256) act_pack_bf16_kernel(const __grid_constan
     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
-      if (s >= p.nsrc) break;
+      if (s >= p.nsrc || c >= p.C) break;
       const hdn_src& S = p.src[s];
       const float* x = S.t.p + hdn_src_off(S, n, d, h, w) + c;
       float4 x0 = __ldg(reinterpret_cast<const float4*>(x)), x1 = __ldg(reinterpret_cast<const float4*>(x + 4));
@@ -307,6 +309,16 @@ __global__ void __launch_bounds__(256) act_pack_bf16_kernel(const __grid_constan
       v0.x += x0.x; v0.y += x0.y; v0.z += x0.z; v0.w += x0.w; v1.x += x1.x; v1.y += x1.y; v1.z += x1.z; v1.w += x1.w;
     }
     uint4 o;
+    if (p.interleave) {
+      uint4 t;
+      tc::pack_split_bf16x2(v0.x, v0.y, o.x, t.x); tc::pack_split_bf16x2(v0.z, v0.w, o.y, t.y);
+      tc::pack_split_bf16x2(v1.x, v1.y, o.z, t.z); tc::pack_split_bf16x2(v1.z, v1.w, o.w, t.w);
+      const int g = c >> 5, j = (c & 31) >> 3;                        // 32-channel group, 8-channel chunk inside it
+      uint4* row = reinterpret_cast<uint4*>(p.out) + m * (long long)(nch * 2) + g * 8;
+      row[j] = o;
+      row[4 + j] = t;
+      continue;
+    }
     if (p.out_lo) {
       uint4 t;
       tc::pack_split_bf16x2(v0.x, v0.y, o.x, t.x); tc::pack_split_bf16x2(v0.z, v0.w, o.y, t.y);
@@ -442,14 +454,15 @@ bool wg2_plan(const hdn_conv* c, Wg2Plan& best) {
 }
 
 int pack_launch(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* out, cudaStream_t st,
-                __nv_bfloat16* out_lo = nullptr) {
+                __nv_bfloat16* out_lo = nullptr, int interleave = 0) {
   PackParams pp;
   memset(&pp, 0, sizeof(pp));
   pp.D = D; pp.H = H; pp.W = W; pp.C = C; pp.nsrc = nsrc;
   for (int i = 0; i < nsrc; ++i) pp.src[i] = srcs[i];
   pp.out = out;
   pp.out_lo = out_lo;
-  pp.total = (long long)N * D * H * W * (C / 8);
+  pp.interleave = interleave;
+  pp.total = (long long)N * D * H * W * (interleave ? (C + 31) / 32 * 4 : C / 8);
   const long long blocks = (pp.total + 255) / 256;
   const unsigned grid = (unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks);
   act_pack_bf16_kernel<<<grid, 256, 0, st>>>(pp);
@@ -460,11 +473,13 @@ int pack_launch(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C
 }  // namespace
 
 // shared with the fprop / dgrad kernel's TMA mode (conv_tc.cu)
-int hdn_tc2_make_map(CUtensorMap* tm, const void* base, int flat, long long M, int N, int D, int H, int W, int C, int bc, int bw, int bh) {
-  return make_map(tm, base, flat, M, N, D, H, W, C, bc, bw, bh, 0);
+int hdn_tc2_make_map(CUtensorMap* tm, const void* base, int flat, long long M, int N, int D, int H, int W, int C, int bc, int bw, int bh,
+                     int swizzle128) {
+  return make_map(tm, base, flat, M, N, D, H, W, C, bc, bw, bh, swizzle128);
 }
-int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {
-  return pack_launch(srcs, nsrc, N, D, H, W, C, hi, st, lo);
+int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st,
+                 int interleave) {
+  return pack_launch(srcs, nsrc, N, D, H, W, C, hi, st, lo, interleave);
 }
 
 // HDN_WGRAD_TC2=0 keeps the first-generation weight-gradient kernel for every shape (default 1)

@@ -10,7 +10,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libhdn.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc2_wgrad.cu", "elementwise.cu", "postproc.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc2_wgrad.cu", "elementwise.cu", "postproc.cu", "augment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -86,6 +86,14 @@ class BnGrad(C.Structure):
                 ("dsbeta", C.c_void_p), ("k0", C.c_void_p), ("k1", C.c_void_p), ("k2", C.c_void_p)]
 
 
+class Aug(C.Structure):
+    _fields_ = [("vol", C.c_void_p), ("seg", C.c_void_p), ("vol_i16", C.c_int32), ("VS", C.c_int32), ("VH", C.c_int32), ("VW", C.c_int32),
+                ("a0", C.c_int32), ("b0", C.c_int32), ("c0", C.c_int32), ("ch", C.c_int32), ("cw", C.c_int32), ("cs", C.c_int32),
+                ("m00", C.c_int32), ("m01", C.c_int32), ("m10", C.c_int32), ("m11", C.c_int32), ("o0", C.c_int32), ("o1", C.c_int32),
+                ("mean", C.c_float), ("out_h", C.c_int32), ("out_w", C.c_int32), ("xs_s", C.c_int64), ("xs_h", C.c_int64), ("xs_w", C.c_int64),
+                ("ys0", C.c_int32), ("yns", C.c_int32)]
+
+
 EXPORTS = [
     "hdn_last_error", "hdn_version", "hdn_conv_fprop", "hdn_conv_dgrad", "hdn_conv_wgrad",
     "hdn_conv_tc_supported", "hdn_conv_tc_workspace", "hdn_conv_tc_plan", "hdn_pool_fwd", "hdn_pool_bwd", "hdn_bn_fold", "hdn_bn_param_grad",
@@ -93,7 +101,7 @@ EXPORTS = [
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
     "hdn_window_accumulate", "hdn_window_finalize", "hdn_dev_malloc", "hdn_dev_free",
     "hdn_ipc_get_handle", "hdn_ipc_open", "hdn_ipc_close", "hdn_set_switch", "hdn_dp_signal", "hdn_dp_wait", "hdn_layout_nhws_to_nshw",
-    "hdn_post_threshold", "hdn_post_dilate", "hdn_post_largest_component", "hdn_post_fill_holes", "hdn_post_and", "hdn_post_compose",
+    "hdn_post_threshold", "hdn_post_dilate", "hdn_post_largest_component", "hdn_post_fill_holes", "hdn_post_and", "hdn_post_compose", "hdn_aug_sample",
 ]
 
 _lib = None
@@ -151,6 +159,7 @@ def load():
         "hdn_post_fill_holes": [vp, vp, i32, i32, i32, vp, i64, vp],
         "hdn_post_and": [vp, vp, vp, i64, vp],
         "hdn_post_compose": [vp, vp, vp, i64, vp],
+        "hdn_aug_sample": [C.POINTER(Aug), vp, vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

@@ -237,8 +237,34 @@ class Model(object):
         ky, ny = self._stage(self._label_array(y), dev, slot)
         return kx, ky, nx + ny
 
+    def _next_staged(self, net, generator, slot):
+        item = next(generator)
+        if getattr(item, "is_device_batch", False):       # augment.CropGenerator: the batch already lies on the device
+            return item
+        return self._stage_batch(net, *item[:2], slot=slot)
+
+    def _consume_device_batch(self, net, batch):
+        """A batch produced on the device (augment.DeviceBatch, engine layout): no host copy, one D2D copy each."""
+        x_dst = list(net.inputs.values())[0].data
+        y_dst = net.loss.labels
+        if batch.x.numel() != x_dst.numel() or batch.y.numel() != y_dst.numel():
+            raise ValueError("device batch %s / %s does not match the model's input %s / labels %s"
+                             % (tuple(batch.x.shape), tuple(batch.y.shape), tuple(x_dst.shape), tuple(y_dst.shape)))
+        cur = torch.cuda.current_stream()
+        cur.wait_event(batch.ready)
+        x_dst.view(batch.x.shape).copy_(batch.x)
+        y_dst.view(batch.y.shape).copy_(batch.y)
+        used = torch.cuda.Event()
+        used.record(cur)
+        batch.release(used)
+        self.h2d_bytes = 0
+
     def _launch_staged(self, net, handle):
         """Enqueue one optimizer step on a staged batch (no host synchronisation); the loss is read by the caller."""
+        if getattr(handle, "is_device_batch", False):
+            self._consume_device_batch(net, handle)
+            self._step_kernels(net)
+            return
         kx, ky, nbytes = handle
         three_d = self.kind != "unet2d"
         self._unstage(kx, list(net.inputs.values())[0].data, three_d)
@@ -304,7 +330,7 @@ class Model(object):
         net = self._net(True)
         total = (int(epochs) - int(initial_epoch)) * int(steps_per_epoch)
         slot, done = 0, 0
-        staged = self._stage_batch(net, *next(generator)[:2], slot=slot) if total > 0 else None
+        staged = self._next_staged(net, generator, slot) if total > 0 else None
         for epoch in range(initial_epoch, epochs):
             losses = []
             t0 = time.time()
@@ -315,7 +341,7 @@ class Model(object):
                 done += 1
                 if done < total:
                     slot ^= 1
-                    staged = self._stage_batch(net, *next(generator)[:2], slot=slot)
+                    staged = self._next_staged(net, generator, slot)
                 losses.append(net.loss.value())
             logs = {"loss": float(np.mean(losses))}
             history["loss"].append(logs["loss"])

@@ -244,6 +244,32 @@ int hdn_post_fill_holes(const unsigned char* in, unsigned char* out, int X, int 
 int hdn_post_and(const unsigned char* a, const unsigned char* b, unsigned char* out, int64_t n, void* stream);
 int hdn_post_compose(const unsigned char* liver, const unsigned char* tumor, unsigned char* out, int64_t n, void* stream);
 
+/* One training sample cut out of a volume that is resident on the device (train_hybrid.py:40-98, train_2ddense.py:40-69:
+ * crop -> mean subtraction -> one of 8 flips / rotations -> skimage `resize` of the label map (order 0, mode 'edge') and
+ * of the image (order 3, mode 'constant', cval 0, clip=True, preserve_range=True) to the network size).
+ * The volume lies slice-major (S, H, W) on the device (the reference holds (H, W, S) host arrays; transposed once at
+ * upload); `vol` is float32 (vol_i16 == 0) or int16, `seg` uint8.
+ * Crop = rows [a0, a0+ch) x columns [b0, b0+cw) x slices [c0, c0+cs).  The flipped crop F is F[i][j] =
+ * crop[m00*i + m01*j + o0][m10*i + m11*j + o1] (a signed permutation; identity = {1,0,0,1,0,0}).
+ * Outputs: x[s*xs_s + y*xs_h + x*xs_w] (fp32, s < cs, y < out_h, x < out_w) and, for slices [ys0, ys0+yns),
+ * y[(s-ys0)*out_h*out_w + y*out_w + x] (fp32 class index); counts[3] (device, int32, may be null) += histogram of the
+ * label values written (train_hybrid.py:126-131 discards a batch that misses a class).
+ * scratch: >= 16 bytes of device memory (crop minimum / maximum for the clip). */
+typedef struct {
+  const void* vol;
+  const unsigned char* seg;
+  int32_t vol_i16;
+  int32_t VS, VH, VW;
+  int32_t a0, b0, c0;
+  int32_t ch, cw, cs;
+  int32_t m00, m01, m10, m11, o0, o1;
+  float mean;
+  int32_t out_h, out_w;
+  int64_t xs_s, xs_h, xs_w;
+  int32_t ys0, yns;
+} hdn_aug;
+int hdn_aug_sample(const hdn_aug* a, float* x, float* y, int32_t* counts, void* scratch, void* stream);
+
 /* Raw device memory + CUDA IPC for the parameter / gradient arenas that the per-GPU
  * processes map into each other (handle = 64 bytes, cudaIpcMemHandle_t). */
 int hdn_dev_malloc(void** out, int64_t bytes);

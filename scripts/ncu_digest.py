@@ -27,7 +27,10 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12}
 
 
 def rows(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    if rep.endswith(".csv"):          # already exported on the GPU box (`ncu -i <rep> --page raw --csv`)
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     lines = [l for l in out.splitlines() if l.startswith('"')]
     r = list(csv.reader(io.StringIO("\n".join(lines))))
     names, units = r[0], r[1]

@@ -7,6 +7,7 @@ Public surface (the reference's builder names):
     DenseUNet161, DenseUNet3d aliases named by the build brief
     SGD, make_parallel, ModelCheckpoint, weighted_crossentropy, weighted_crossentropy_2ddense
     predict_tumor_inwindow    lib.funcs.predict_tumor_inwindow
+    augment.DeviceVolumes / augment.CropGenerator   generate_arrays_from_file of the training scripts, on the device
 The import name is `h_denseunet_b200` (the directory carries the project's hyphenated name).
 """
 from .builders import (DenseUNet, DenseUNet161, DenseUNet3d, DenseNet3D, dense_rnn_net, denseunet_3d, Scale)
@@ -14,7 +15,7 @@ from .keras_api import (Model, SGD, ModelCheckpoint, make_parallel, weighted_cro
                         weighted_crossentropy_2ddense)
 from .inference import predict_tumor_inwindow
 from .postprocess import postprocess_scores
-from . import keras_api, keras_h5, h5lite, preprocessing
+from . import keras_api, keras_h5, h5lite, preprocessing, augment
 
 __all__ = ["DenseUNet", "DenseUNet161", "DenseUNet3d", "DenseNet3D", "dense_rnn_net", "denseunet_3d", "Scale",
            "Model", "SGD", "ModelCheckpoint", "make_parallel", "weighted_crossentropy",

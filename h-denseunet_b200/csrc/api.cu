@@ -30,6 +30,7 @@ void hdn_wgrad_tc2_set(int v);
 void hdn_tc2_layout_set(int v);
 void hdn_tc_tma_set(int v);
 void hdn_tc_sw128_set(int v);
+void hdn_tc_x3fold_set(int v);
 int hdn_wgrad_tc2_supported(const hdn_conv* c);
 long long hdn_wgrad_tc2_workspace(const hdn_conv* c);
 int hdn_wgrad_tc2_plan_info(const hdn_conv* c, int* out);
@@ -57,6 +58,7 @@ extern "C" int hdn_set_switch(const char* name, int value) {
   if (!strcmp(name, "HDN_TC2_LAYOUT")) { hdn_tc2_layout_set(value); return HDN_OK; }
   if (!strcmp(name, "HDN_TC_TMA")) { hdn_tc_tma_set(value); return HDN_OK; }
   if (!strcmp(name, "HDN_TC_SW128")) { hdn_tc_sw128_set(value); return HDN_OK; }
+  if (!strcmp(name, "HDN_TC_X3FOLD")) { hdn_tc_x3fold_set(value); return HDN_OK; }
   hdn_set_error("set_switch: unknown switch %s", name);
   return HDN_ERR_ARG;
 }

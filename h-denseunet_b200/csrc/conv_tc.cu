@@ -48,13 +48,8 @@ int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int 
 
 namespace {
 
-// -DHDN_TC_X3FOLD compiles the folded bf16x3 issue scheme in (experiment, see TcParams::fold); without it the code is
-// absent and the kernel is the one validated on B200 in round 1
-#ifdef HDN_TC_X3FOLD
+// The folded bf16x3 issue scheme (TcParams::fold) is a run-time switch (HDN_TC_X3FOLD / hdn_set_switch)
 constexpr bool kFold = true;
-#else
-constexpr bool kFold = false;
-#endif
 
 constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
 constexpr int NPROD = 256;        // producer threads
@@ -64,6 +59,10 @@ constexpr int NSB_MAX = 16;   // weight-block ring depth upper bound
 constexpr int NTAB = 4;       // geometry-table buffers (the copy front runs at most 3 stages ahead of the transform)
 constexpr int UB = 2;         // direct (space-to-depth) producer: pixel groups loaded ahead per warp
 constexpr int EPI_BYTES = 32 * 33 * 4 + 4 * 32 * 8;   // per epilogue warp: transpose tile + 4 row-offset tables
+#ifndef HDN_FB
+#define HDN_FB 4
+#endif
+constexpr int FB = HDN_FB;      // fprop epilogue: rows of the transpose tile a lane reads ahead of its stores
 constexpr int MAXC0 = 14;     // copies per producer thread and stage, source 0 (4-tap stems' dgrad: 19x11 px x 16 quads / 256 threads)
 constexpr int MAXC1 = 6;      // ... source 1 (only with 32-channel stages: 180 px x 8 quads / 256)
 
@@ -809,6 +808,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const bool do_stats = p.stat_sum != nullptr;
         const bool has_bias = p.bias != nullptr, drop = p.drop_keep < 1.0f;
         float* ybase = const_cast<float*>(p.y.p) + p.y.coff;
+        // 16-byte stores need quads that are all-in or all-out and 16-byte aligned rows
+        const bool vec_ok = ((p.NC | p.BN | p.y.ldc | p.y.coff) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0;
         ro0[lane] = m * (long long)p.y.ldc;
         rod[lane] = m;                                      // linear position (dropout hash index)
         const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
@@ -825,21 +826,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int i = 0; i < 16; ++i) tT[lane * 33 + 16 + i] = v2[i];
           }
           __syncwarp();
-          const int col = n_tile * p.BN + cb + lane;
-          const bool cok = lane < ncols && col < p.NC;
-          const float bias = (has_bias && cok) ? __ldg(p.bias + col) : 0.f;
-          float ssum = 0.f, ssq = 0.f;
-          if (cok) {
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-              if (!((vmask >> rr) & 1u)) continue;             // warp-uniform
-              float tv = tT[rr * 33 + lane] + bias;
-              const long long ro = ro0[rr];
-              if (drop) tv *= hdn_drop_scale(p.drop_seed, (uint64_t)rod[rr] * p.NC + col, p.drop_keep);
-              ybase[ro + col] = tv;
-              ssum += tv; ssq += tv * tv;
+          if (vec_ok) {
+            // Quad form (as in the data-gradient epilogue): lane = (row sub-index, channel quad).  The four rows of a batch
+            // are read from the transpose tile BEFORE the first store is issued -- a store through the generic output
+            // pointer orders every later shared-memory load behind it, which made the scalar form pay a full LDS round trip
+            // per output row (78 cycles per row, 15k cycles per 128 x 192 tile: profiles/r02j_role_timing.txt) -- and a row
+            // leaves as one 16-byte store per lane.
+            const int rsub = lane >> 3, cq = lane & 7;
+            const int col4 = n_tile * p.BN + cb + 4 * cq;
+            const bool qok = 4 * cq < ncols && col4 < p.NC;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_bias && qok) bias4 = make_float4(__ldg(p.bias + col4), __ldg(p.bias + col4 + 1), __ldg(p.bias + col4 + 2), __ldg(p.bias + col4 + 3));
+            float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+#pragma unroll
+            for (int it0 = 0; it0 < 8; it0 += FB) {
+              float4 tv[FB];
+              long long ro[FB], rp[FB];
+#pragma unroll
+              for (int k = 0; k < FB; ++k) {
+                const int rr = 4 * (it0 + k) + rsub;
+                const float* tp = tT + rr * 33 + 4 * cq;
+                tv[k] = make_float4(tp[0], tp[1], tp[2], tp[3]);
+                ro[k] = ro0[rr];
+                rp[k] = rod[rr];
+              }
+#pragma unroll
+              for (int k = 0; k < FB; ++k) {
+                const int rr = 4 * (it0 + k) + rsub;
+                if (!(qok && ((vmask >> rr) & 1u))) continue;
+                float4 t4 = make_float4(tv[k].x + bias4.x, tv[k].y + bias4.y, tv[k].z + bias4.z, tv[k].w + bias4.w);
+                if (drop) {
+                  const uint64_t di = (uint64_t)rp[k] * p.NC + col4;
+                  t4.x *= hdn_drop_scale(p.drop_seed, di, p.drop_keep);
+                  t4.y *= hdn_drop_scale(p.drop_seed, di + 1, p.drop_keep);
+                  t4.z *= hdn_drop_scale(p.drop_seed, di + 2, p.drop_keep);
+                  t4.w *= hdn_drop_scale(p.drop_seed, di + 3, p.drop_keep);
+                }
+                *reinterpret_cast<float4*>(ybase + ro[k] + col4) = t4;
+                s1.x += t4.x; s1.y += t4.y; s1.z += t4.z; s1.w += t4.w;
+                s2.x += t4.x * t4.x; s2.y += t4.y * t4.y; s2.z += t4.z * t4.z; s2.w += t4.w * t4.w;
+              }
             }
-            if (do_stats) { atomicAdd(&st_[cb + lane], ssum); atomicAdd(&st_[p.BN + cb + lane], ssq); }
+            if (do_stats) {
+#pragma unroll
+              for (int o = 8; o <= 16; o <<= 1) {
+                s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o); s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                s1.z += __shfl_xor_sync(0xffffffffu, s1.z, o); s1.w += __shfl_xor_sync(0xffffffffu, s1.w, o);
+                s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+                s2.z += __shfl_xor_sync(0xffffffffu, s2.z, o); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, o);
+              }
+              if (rsub == 0 && qok) {
+                float* p1 = &st_[cb + 4 * cq];
+                float* p2 = &st_[p.BN + cb + 4 * cq];
+                atomicAdd(p1, s1.x); atomicAdd(p1 + 1, s1.y); atomicAdd(p1 + 2, s1.z); atomicAdd(p1 + 3, s1.w);
+                atomicAdd(p2, s2.x); atomicAdd(p2 + 1, s2.y); atomicAdd(p2 + 2, s2.z); atomicAdd(p2 + 3, s2.w);
+              }
+            }
+          } else {
+            const int col = n_tile * p.BN + cb + lane;
+            const bool cok = lane < ncols && col < p.NC;
+            const float bias = (has_bias && cok) ? __ldg(p.bias + col) : 0.f;
+            float ssum = 0.f, ssq = 0.f;
+            if (cok) {
+  #pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr) {
+                if (!((vmask >> rr) & 1u)) continue;             // warp-uniform
+                float tv = tT[rr * 33 + lane] + bias;
+                const long long ro = ro0[rr];
+                if (drop) tv *= hdn_drop_scale(p.drop_seed, (uint64_t)rod[rr] * p.NC + col, p.drop_keep);
+                ybase[ro + col] = tv;
+                ssum += tv; ssq += tv * tv;
+              }
+              if (do_stats) { atomicAdd(&st_[cb + lane], ssum); atomicAdd(&st_[p.BN + cb + lane], ssq); }
+            }
           }
           __syncwarp();
         }
@@ -919,12 +978,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               if (wr_) {
                 const char* px = reinterpret_cast<const char*>(S.t.p + ms * (long long)S.t.ldc + S.t.coff + tn.n_tile * p.BN);
                 for (int o = 0; o < ncb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
-                const hdn_dgrad_epi& E = p.epi[e];
-                if (E.accumulate && S.ud != 2) {                     // the old gradient values of the read-modify-write form
-                  const char* pg = E.mode == 0 ? reinterpret_cast<const char*>(E.dx.p + ms * (long long)E.dx.ldc + E.dx.coff + tn.n_tile * p.BN)
-                                               : reinterpret_cast<const char*>(E.du + ms * (long long)p.NC + tn.n_tile * p.BN);
-                  for (int o = 0; o < ncb; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + o));
-                }
               }
             }
           }
@@ -967,25 +1020,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const long long* rd = rod + e * 32;
               const unsigned wm = wmask[e];
               float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-              // An accumulating write that no other CTA touches (everything but a depth-up-sampled source) is a plain
-              // load + add + store: the reduction unit retires ~1 element per cycle per SM, which bounded the dense blocks'
-              // 1x1 data gradients (measured 63k cycles of epilogue per 128 x 240 tile, profiles/r02j_role_timing.txt);
-              // the old values are fetched in the same batch as the stored activations.
-              const bool rmw = acc && !atom;
-              for (int it0 = 0; it0 < 8; it0 += 2) {             // batches of 2 rows: 2 stored values + 2 old gradients in flight
-                float4 xs[2], os[2];
+              // An accumulating write is a fire-and-forget vector reduction (executes in L2, no read latency on the SM side).  The
+              // read-modify-write alternative (load old gradient, add, store) was measured slower on every layer -- dense2_x1
+              // 1.45 -> 2.32 ms, fianl_conv 2.39 -> 2.80 ms (profiles/r02l_dgrad_red_vs_rmw.txt): the extra 16-byte load per
+              // row doubles what a lane has to keep in flight.
+              // two batches of 4 rows: the 4 stored-value loads of a batch are in flight together
+              for (int it0 = 0; it0 < 8; it0 += 4) {
+                float4 xs[4];
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < 4; ++k) {
                   const int rr = 4 * (it0 + k) + rsub;
                   xs[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                  os[k] = xs[k];
-                  if (qok && ((wm >> rr) & 1u)) {
-                    xs[k] = ldg4(xb + rx[rr] + col4);
-                    if (rmw) os[k] = *reinterpret_cast<const float4*>(db + rd[rr] + col4);
-                  }
+                  if (qok && ((wm >> rr) & 1u)) xs[k] = ldg4(xb + rx[rr] + col4);
                 }
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < 4; ++k) {
                   const int rr = 4 * (it0 + k) + rsub;
                   if (!(qok && ((wm >> rr) & 1u))) continue;
                   const float* tp = tT + rr * 33 + 4 * cq;
@@ -1006,10 +1055,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   s2.x += dz.x * (x.x - c4.x); s2.y += dz.y * (x.y - c4.y); s2.z += dz.z * (x.z - c4.z); s2.w += dz.w * (x.w - c4.w);
                   float* q = db + rd[rr] + col4;
                   const float4 g = make_float4(ga.x * dz.x, ga.y * dz.y, ga.z * dz.z, ga.w * dz.w);
-                  if (atom)
+                  if (atom | acc)
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(g.x), "f"(g.y), "f"(g.z), "f"(g.w) : "memory");
                   else
-                    *reinterpret_cast<float4*>(q) = make_float4(g.x + os[k].x, g.y + os[k].y, g.z + os[k].z, g.w + os[k].w);
+                    *reinterpret_cast<float4*>(q) = g;
                 }
               }
               if (E.s1) {                                                // (warp-uniform) fold the 4 row sub-indices of a quad
@@ -1231,15 +1280,17 @@ int hdn_tc_fastx() {
   return v;
 }
 
-// HDN_TC_X3FOLD=1 (and a library built with -DHDN_TC_X3FOLD): experiment switch, see TcParams::fold (default 0)
+// HDN_TC_X3FOLD=1: folded bf16x3 (A_hi x [B_hi | B_lo] as one MMA of N = 2*BN, + A_lo x B_hi): 2 MMAs and 14 KB of
+// shared-memory operand reads per K step instead of 3 MMAs and 18 KB (BN = 64); see TcParams::fold.  Also hdn_set_switch().
+static int g_tc_x3fold = -1;
 int hdn_tc_x3fold() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_tc_x3fold < 0) {
     const char* e = getenv("HDN_TC_X3FOLD");
-    v = (e && atoi(e) != 0) ? 1 : 0;
+    g_tc_x3fold = (e && atoi(e) != 0) ? 1 : 0;
   }
-  return v;
+  return g_tc_x3fold;
 }
+void hdn_tc_x3fold_set(int v) { g_tc_x3fold = v ? 1 : 0; }
 
 // Tails of the bf16x3 operands as IEEE half instead of bfloat16 (3 more significant bits per operand) would need MMAs
 // that pair a bf16 operand with an f16 one.  The instruction descriptor has separate A / B format fields, but sm_100a
@@ -1396,7 +1447,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   pl.tab_ints = toff;
   const size_t a_bytes = pl.sw ? ((size_t)pl.P * 128 + 1023) / 1024 * 1024 : 8ull * pl.Ppad * 16;
   const size_t b_bytes = (size_t)pl.BN * pl.CK * 2 * nsplit;
-  pl.fold = (kFold && nsplit == 2 && hdn_tc_x3fold() && pl.BN <= 128) ? 1 : 0;
+  pl.fold = (kFold && nsplit == 2 && hdn_tc_x3fold() && pl.BN <= 128 && !pl.sw) ? 1 : 0;
   int cols = 32;
   while (cols < 2 * pl.BN * (pl.fold ? 2 : 1)) cols *= 2;  // two accumulator buffers
   pl.tmem_cols = cols;

@@ -21,7 +21,12 @@
  *       HDN_TC_FASTX=0|1|2  operand-transform form of the tcgen05 kernels (default 2)
  *       HDN_POOL_FAST=0|1   vector max-pool backward (default 1)
  *       HDN_TC_L2PF=0|1     L2::256B prefetch hint on the raw patch copies (default 0, experiment)
- *       HDN_TC_X3FOLD=0|1   folded bf16x3 issue scheme (default 0, experiment; needs a -DHDN_TC_X3FOLD build)
+ *       HDN_TC_X3FOLD=0|1   folded bf16x3 issue scheme: A_hi x [B_hi | B_lo] as one MMA of N = 2*BN plus A_lo x B_hi
+ *                           (2 MMAs per K step instead of 3; layers with BN <= 128); also hdn_set_switch()
+ *       HDN_TC_TMA=0|1|2    fprop / dgrad operand path: bf16 pre-pass + TMA tile loads for no layer / the 3x3(x3) layers /
+ *                           all stride-1 layers (default 2); also hdn_set_switch()
+ *       HDN_TC_SW128=0|1    TMA mode with 128-byte swizzled K-major operand rows instead of 16-byte chunk planes
+ *                           (default 0: measured equal, profiles/r02l_*); also hdn_set_switch()
  *       HDN_WGRAD_TC2=0|1   weight gradients of the 1x3x3 / 3x3x3 convolutions (precision 1) through the bf16 pre-pass +
  *                           TMA tile-load kernel (default 1; 0 = first-generation kernel); also hdn_set_switch()
  *       HDN_TC2_LAYOUT=0|1  shared-memory operand layout of that kernel: 0 = 16-byte chunk planes (SWIZZLE_NONE),

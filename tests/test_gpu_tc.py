@@ -333,3 +333,30 @@ def test_fprop_dgrad_tma_swizzle128(cuda_dev, name, prec):
                     assert rel_l2(S1[0], S0[0]) < TOL and rel_l2(S1[1], S0[1]) < TOL
     finally:
         _switch("HDN_TC_SW128", 0)
+
+
+@pytest.mark.parametrize("name", TMA_CASES)
+def test_fprop_dgrad_x3_folded(cuda_dev, name):
+    """HDN_TC_X3FOLD=1: bf16x3 as two MMAs per K step -- A_hi x [B_hi | B_lo] with N = 2*BN into a double-width accumulator
+    (the halves are added when the epilogue reads TMEM) and A_lo x B_hi."""
+    kw = dict(CASES[name])
+    kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
+    _switch("HDN_TC_X3FOLD", 1)
+    try:
+        c = Case(cuda_dev, tc=2, **kw)
+        TOL = TOLS[2]
+        y0, s0, _ = c.fprop(0)
+        y1, s1, untouched = c.fprop(2)
+        assert untouched == 0.0
+        assert rel_l2(y1, y0) < TOL, (name, rel_l2(y1, y0))
+        if s0 is not None:
+            assert rel_l2(s1[0], s0[0]) < TOL and rel_l2(s1[1], s0[1]) < TOL
+        if name in DG:
+            for mode, acc in ((0, False), (0, True), (1, True)):
+                r0 = c.dgrad(0, mode, acc)
+                r1 = c.dgrad(2, mode, acc)
+                for (g0, S0), (g1, S1) in zip(r0, r1):
+                    assert rel_l2(g1, g0) < TOL, (name, mode, acc, rel_l2(g1, g0))
+                    assert rel_l2(S1[0], S0[0]) < TOL and rel_l2(S1[1], S0[1]) < TOL
+    finally:
+        _switch("HDN_TC_X3FOLD", 0)

@@ -9,7 +9,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libhdn.so")
+# HDN_LIB: load another build of the same sources (A/B variants of a kernel timed side by side, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("HDN_LIB") or os.path.join(_HERE, "libhdn.so")
 SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_wgrad.cu", "conv_tc2_wgrad.cu", "elementwise.cu", "postproc.cu", "augment.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

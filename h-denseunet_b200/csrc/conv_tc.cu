@@ -48,8 +48,19 @@ int hdn_tc2_pack(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int 
 
 namespace {
 
-// The folded bf16x3 issue scheme (TcParams::fold) is a run-time switch (HDN_TC_X3FOLD / hdn_set_switch)
+// The folded bf16x3 issue scheme (TcParams::fold) is a run-time switch (HDN_TC_X3FOLD / hdn_set_switch).
+// -DHDN_NO_FOLD / -DHDN_FPROP_SCALAR build A/B variants of the kernel without the fold code / with the scalar fprop
+// epilogue (scripts/build_variants.sh; timings of the variants side by side on one box: profiles/r02n_variants.txt).
+#ifdef HDN_NO_FOLD
+constexpr bool kFold = false;
+#else
 constexpr bool kFold = true;
+#endif
+#ifdef HDN_FPROP_SCALAR
+constexpr bool kFpropQuad = false;
+#else
+constexpr bool kFpropQuad = true;
+#endif
 
 constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
 constexpr int NPROD = 256;        // producer threads
@@ -809,7 +820,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const bool has_bias = p.bias != nullptr, drop = p.drop_keep < 1.0f;
         float* ybase = const_cast<float*>(p.y.p) + p.y.coff;
         // 16-byte stores need quads that are all-in or all-out and 16-byte aligned rows
-        const bool vec_ok = ((p.NC | p.BN | p.y.ldc | p.y.coff) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0;
+        const bool vec_ok = kFpropQuad && ((p.NC | p.BN | p.y.ldc | p.y.coff) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y.p) & 15) == 0;
         ro0[lane] = m * (long long)p.y.ldc;
         rod[lane] = m;                                      // linear position (dropout hash index)
         const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);

@@ -217,12 +217,19 @@ __device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q,
   if (qok) *reinterpret_cast<uint4*>(dst + (uint32_t)chunk * ppad * 16u + (uint32_t)q * 16u) = o;
 }
 
+// Instantiated per (pass, folded bf16x3, operand path): the warp roles of one instance share a register allocation (128 per
+// thread), and code that an instance never runs still costs it -- with the fold and the SIMT-producer code compiled into
+// every launch the 3x3(x3) layers ran 7 % slower (profiles/r02n_variants.txt: one box, five builds side by side).
+//   MODE 0 fprop, 1 dgrad;  FOLD: TcParams::fold;  OPER 0 SIMT producers (stems), 1 TMA chunk planes, 2 TMA 128-byte swizzled rows
+template <int MODE, bool FOLD, int OPER>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool TMA = OPER != 0;
+  constexpr bool SW = OPER == 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the 128-byte swizzle is a function of the shared-memory address bits 4-9: stages start on 1024-byte boundaries
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t A_BYTES = p.sw ? (((uint32_t)p.P * 128u + 1023u) & ~1023u) : 8u * p.Ppad * 16u;
+  const uint32_t A_BYTES = SW ? (((uint32_t)p.P * 128u + 1023u) & ~1023u) : 8u * p.Ppad * 16u;
   const uint32_t B_HALF = (uint32_t)p.BN * (uint32_t)p.CK * 2u;          // one bf16 weight block
   const uint32_t B_BYTES = p.split ? 2u * B_HALF : B_HALF;                 // bf16x3: head block | tail block
   const int nsa = p.nsa;
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < MAXNSA; ++i) { tc::mbar_init(&a_full[i], p.tma ? 1 : NPROD); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < MAXNSA; ++i) { tc::mbar_init(&a_full[i], TMA ? 1 : NPROD); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB_MAX; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
     tc::fence_barrier_init();
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     int sa = 0;
     uint32_t pha = 0;
 
-    if (p.tma) {
+    if (TMA) {
       // ---- TMA mode: the operand is already bf16 in global memory; warp 0 (converged, one elected lane issuing) stages one
       // chunk plane per box.  Zero padding, image borders and channel tails are the copy engine's out-of-bounds fill.
       if (warp == 0) {
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t box_bytes = (uint32_t)p.P * 16u;
         while (!tr.done) {
           tc::mbar_wait(&a_empty[sa], pha ^ 1);
-          if (p.sw) {
+          if (SW) {
             if (tc::elect_one_sync()) {
               uint8_t* dst = sA + sa * A_BYTES;
               tc::mbar_arrive_expect_tx(&a_full[sa], (uint32_t)p.P * 128u);
@@ -632,12 +639,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t acc = 0, tmem_d = tmem_base;
       // SWIZZLE_128B form: rows (pixels / output channels) are 128 bytes, 8-row groups SBO apart, K advances inside the row
       const uint64_t sw_bit = (uint64_t)2 << 61;
-      const uint64_t adesc_hi = p.sw ? (tc::make_smem_desc(0, 16u, (uint32_t)p.PW * 128u) | sw_bit) : tc::make_smem_desc(0, lbo_a, sbo_a);
-      const uint64_t bdesc_hi = p.sw ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, lbo_b, sbo_b);
-      const uint64_t kstep_a = p.sw ? 2u : (uint64_t)((2u * lbo_a) >> 4), kstep_b = p.sw ? 2u : (uint64_t)((2u * lbo_b) >> 4);
-      const uint64_t tail_a = p.sw ? 4u : (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_a) >> 4);
-      const uint64_t tail_b = p.sw ? 4u : (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_b) >> 4);
-      const uint32_t pixu = p.sw ? 8u : 1u;                  // 16-byte units per patch pixel
+      const uint64_t adesc_hi = SW ? (tc::make_smem_desc(0, 16u, (uint32_t)p.PW * 128u) | sw_bit) : tc::make_smem_desc(0, lbo_a, sbo_a);
+      const uint64_t bdesc_hi = SW ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, lbo_b, sbo_b);
+      const uint64_t kstep_a = SW ? 2u : (uint64_t)((2u * lbo_a) >> 4), kstep_b = SW ? 2u : (uint64_t)((2u * lbo_b) >> 4);
+      const uint64_t tail_a = SW ? 4u : (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_a) >> 4);
+      const uint64_t tail_b = SW ? 4u : (uint64_t)(((uint32_t)(p.CK >> 3) * lbo_b) >> 4);
+      const uint32_t pixu = SW ? 8u : 1u;                  // 16-byte units per patch pixel
       // folded bf16x3: chunk stride of the [head | tail] weight block is 2*BN rows; N = 2*BN for A_hi, N = BN for A_lo
       const uint32_t idesc_f2 = tc::make_idesc_bf16(128, 2 * p.BN, 0, 0);
       const uint64_t bdesc_hi_f = tc::make_smem_desc(0, 2u * lbo_b, sbo_b), kstep_b_f = (uint64_t)((4u * lbo_b) >> 4);
@@ -649,7 +656,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           const int ab = cur_seq & 1;
           tc::mbar_wait(&acc_empty[ab], ((uint32_t)(cur_seq >> 1) & 1u) ^ 1u);
           tc::tc_fence_after();
-          tmem_d = tmem_base + (uint32_t)(ab * ((kFold && p.fold) ? 2 * p.BN : p.BN));
+          tmem_d = tmem_base + (uint32_t)(ab * (FOLD ? 2 * p.BN : p.BN));
           acc = 0;
         }
         const int cv = min(p.CK, p.K - it.kb * p.CK);
@@ -676,7 +683,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
             if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
             if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
-          } else if (kFold && p.fold) {
+          } else if (FOLD) {
             const uint64_t bdf = bdesc_hi_f | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
             for (int s = 0; s < nk; ++s) {
               const uint64_t ah = ad + (uint64_t)s * kstep_a, bf = bdf + (uint64_t)s * kstep_b_f;
@@ -745,7 +752,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int i = etid; i < 4 * p.BN; i += 128) dstat[i] = 0.0;
     int flush_ntile = -1;
     auto flush_stats = [&](int nt) {
-      if (p.mode == 0) {
+      if (MODE == 0) {
         for (int c = etid; c < p.BN; c += 128) {
           const int col = nt * p.BN + c;
           if (col < p.NC) { atomicAdd(p.stat_sum + col, dstat[c]); atomicAdd(p.stat_sq + col, dstat[p.BN + c]); }
@@ -785,7 +792,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         m = (((long long)t.n_img * p.D + t.d0) * p.H + oh) * p.W + ow;
       }
       bool any_s = false;
-      if (p.mode == 0) any_s = p.stat_sum != nullptr;
+      if (MODE == 0) any_s = p.stat_sum != nullptr;
       else if (!p.scatter)
         for (int e = 0; e < p.nepi; ++e) any_s = any_s || (p.epi[e].mode != 2 && p.epi[e].s1 != nullptr);
       if (any_s) {
@@ -800,11 +807,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #ifdef HDN_TC_TIMING
       te_wait += clock64() - te0; te0 = clock64();
 #endif
-      const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * ((kFold && p.fold) ? 2 * p.BN : p.BN));
+      const uint32_t taddr = tmem_base + ((uint32_t)(qtr * 32) << 16) + (uint32_t)(ab * (FOLD ? 2 * p.BN : p.BN));
       // accumulator columns [col, col+16) of this lane's row; folded bf16x3 adds the A_hi x B_lo half BN columns further
       auto ld_acc = [&](int col, float* dst) {
         tc::tmem_ld16(taddr + (uint32_t)col, dst);
-        if (kFold && p.fold) {
+        if (FOLD) {
           float w2[16];
           tc::tmem_ld16(taddr + (uint32_t)(p.BN + col), w2);
 #pragma unroll
@@ -812,7 +819,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       };
 
-      if (p.mode == 0) {
+      if (MODE == 0) {
         // Transposed epilogue: the warp's 32 x 32 accumulator block goes through shared memory so that lane = output
         // channel and the 32 lanes write 128 contiguous bytes of one output pixel; the per-channel batch statistics
         // become plain per-lane running sums (no shuffles).
@@ -1458,7 +1465,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   pl.tab_ints = toff;
   const size_t a_bytes = pl.sw ? ((size_t)pl.P * 128 + 1023) / 1024 * 1024 : 8ull * pl.Ppad * 16;
   const size_t b_bytes = (size_t)pl.BN * pl.CK * 2 * nsplit;
-  pl.fold = (kFold && nsplit == 2 && hdn_tc_x3fold() && pl.BN <= 128 && !pl.sw) ? 1 : 0;
+  pl.fold = (kFold && nsplit == 2 && hdn_tc_x3fold() && pl.BN <= 128 && pl.tma && !pl.sw) ? 1 : 0;
   int cols = 32;
   while (cols < 2 * pl.BN * (pl.fold ? 2 : 1)) cols *= 2;  // two accumulator buffers
   pl.tmem_cols = cols;
@@ -1505,6 +1512,33 @@ TcPlan tc_plan(const hdn_conv* c, const TcGeom& g, int mode) {
   return pl;
 }
 
+template <int MODE, bool FOLD, int OPER>
+int tc_run(unsigned grid, size_t smem, cudaStream_t st, const TcParams& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<MODE, FOLD, OPER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { hdn_set_error("conv tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
+    attr_set = true;
+  }
+  conv_tc_kernel<MODE, FOLD, OPER><<<grid, TC_THREADS, smem, st>>>(p);
+  return HDN_OK;
+}
+int tc_dispatch(int mode, int fold, int oper, unsigned grid, size_t smem, cudaStream_t st, const TcParams& p) {
+  const int key = (mode ? 1 : 0) * 100 + (fold ? 1 : 0) * 10 + oper;
+  switch (key) {
+    case 0: return tc_run<0, false, 0>(grid, smem, st, p);
+    case 1: return tc_run<0, false, 1>(grid, smem, st, p);
+    case 2: return tc_run<0, false, 2>(grid, smem, st, p);
+    case 11: return tc_run<0, true, 1>(grid, smem, st, p);
+    case 100: return tc_run<1, false, 0>(grid, smem, st, p);
+    case 101: return tc_run<1, false, 1>(grid, smem, st, p);
+    case 102: return tc_run<1, false, 2>(grid, smem, st, p);
+    case 111: return tc_run<1, true, 1>(grid, smem, st, p);
+  }
+  hdn_set_error("conv tc: no kernel instance for pass %d fold %d operand path %d", mode, fold, oper);
+  return HDN_ERR_UNSUPPORTED;
+}
+
 int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_t st) {
   const TcGeom g = tc_geom(c, mode);
   const TcPlan pl = tc_plan(c, g, mode);
@@ -1514,12 +1548,6 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
                 "conv tc: patch of %d / %d pixels exceeds the per-thread copy list", pl.Ps[0], pl.Ps[1]);
   HDN_CHECK_ARG(c->ws != nullptr && c->ws_bytes >= pl.ws_elems * 2, "conv tc: workspace too small (%lld < %lld bytes)",
                 (long long)c->ws_bytes, (long long)pl.ws_elems * 2);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { hdn_set_error("conv tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
-    attr_set = true;
-  }
   const long long w_bytes = (pl.ws_elems * 2 + 255) / 256 * 256;
   const long long op_bytes = pl.tma ? (pl.op_elems * 2 + 255) / 256 * 256 : 0;
   HDN_CHECK_ARG(!pl.tma || (c->ws_bytes >= w_bytes + op_bytes * nsplit && (reinterpret_cast<uintptr_t>(c->ws) & 255) == 0),
@@ -1637,7 +1665,10 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
   const unsigned grid = (unsigned)(p.total_work < num_sms ? p.total_work : num_sms);   // persistent: one CTA per SM
-  conv_tc_kernel<<<grid, TC_THREADS, pl.smem, st>>>(p);
+  const int oper = pl.tma ? (pl.sw ? 2 : 1) : 0;
+  HDN_CHECK_ARG(!(pl.fold && oper != 1), "conv tc: the folded bf16x3 form exists for the chunk-plane TMA mode only");
+  const int rc = tc_dispatch(mode, pl.fold, oper, grid, pl.smem, st, p);
+  if (rc != HDN_OK) return rc;
   HDN_CHECK_LAUNCH(mode == 0 ? "conv_fprop_tc" : "conv_dgrad_tc");
   return HDN_OK;
 }

@@ -48,14 +48,29 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a, long long* out
       __syncwarp();
       t0 = clock64();
       if (tc::elect_one_sync()) {
-        for (int i = 0; i < a.R; ++i) {
-          const uint32_t k = (uint32_t)(i % a.nbuf);
-          const uint32_t sh = a.shift ? (uint32_t)((i * 7) % 19) * (a.layout ? 128u : 16u) : 0u;
-          const uint64_t ad = ad0 | (uint64_t)(((sA + k * a_stride + sh) >> 4) & 0x3FFF);
-          const uint64_t bd = bd0 | (uint64_t)(((sB + (k % (a.layout ? 2u : 4u)) * b_stride) >> 4) & 0x3FFF);
-          const uint32_t d = tm + ((a.ts && a.N > 192) ? 0u : (uint32_t)((i & 1) * a.N));
-          if (a.ts) umma_ts(d, tm + 480u + (k & 3u) * 8u, bd, idesc, 1u);
-          else tc::umma_bf16(d, ad, bd, idesc, 1u);
+        // descriptors are loop invariants: the loop body is four MMAs and a counter (an earlier version of this benchmark
+        // computed them per iteration with integer divisions and measured its own address arithmetic: ~105 cycles per MMA)
+        uint64_t ad[4], bd[4];
+        uint32_t ta[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t k = (uint32_t)(u % a.nbuf);
+          const uint32_t sh = a.shift ? (uint32_t)((u * 7 + 3) % 19) * (a.layout ? 128u : 16u) : 0u;
+          ad[u] = ad0 | (uint64_t)(((sA + k * a_stride + sh) >> 4) & 0x3FFF);
+          bd[u] = bd0 | (uint64_t)(((sB + (k % (a.layout ? 2u : 4u)) * b_stride) >> 4) & 0x3FFF);
+          ta[u] = tm + 480u + (k & 3u) * 8u;
+        }
+        const uint32_t d0 = tm, d1 = tm + ((a.ts && a.N > 192) ? 0u : (uint32_t)a.N);
+        if (a.ts) {
+          for (int i = 0; i < a.R; i += 4) {
+            umma_ts(d0, ta[0], bd[0], idesc, 1u); umma_ts(d1, ta[1], bd[1], idesc, 1u);
+            umma_ts(d0, ta[2], bd[2], idesc, 1u); umma_ts(d1, ta[3], bd[3], idesc, 1u);
+          }
+        } else {
+          for (int i = 0; i < a.R; i += 4) {
+            tc::umma_bf16(d0, ad[0], bd[0], idesc, 1u); tc::umma_bf16(d1, ad[1], bd[1], idesc, 1u);
+            tc::umma_bf16(d0, ad[2], bd[2], idesc, 1u); tc::umma_bf16(d1, ad[3], bd[3], idesc, 1u);
+          }
         }
         tc::umma_commit(&bar);
       }

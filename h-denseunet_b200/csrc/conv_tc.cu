@@ -89,6 +89,7 @@ struct TcParams {
   int kd, kh, kw;
   int K, NC;                  // contraction channels, output columns
   int BN, KB, CK, nsb, nraw, tmem_cols;
+  int ub;                     // filter taps per weight-ring unit: one bulk copy, one full / empty barrier pair (nsb % ub == 0)
   int flat;                   // 1: rows are 128 consecutive linear positions (1x1x1, no up-sampling)
   int PH, PW, P, Ppad;        // virtual patch rows, cols, pixels, padded (odd) pixel count
   int PHs[2], PWs[2], Ps[2];  // source-resolution patch of each source
@@ -607,16 +608,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       int sb = 0;
       uint32_t phb = 0;
       const size_t blk = (size_t)p.BN * p.CK * (p.split ? 2 : 1);
+      const int nsu = p.nsb / p.ub;                         // ring depth in units
       while (!it.done) {
         const __nv_bfloat16* src = p.wpack + (((size_t)it.t.n_tile * p.KB + it.kb) * T + (size_t)it.dz * taps_hw) * blk;
-        for (int t2 = 0; t2 < taps_hw; ++t2, src += blk) {
+        for (int t2 = 0; t2 < taps_hw; t2 += p.ub, src += (size_t)p.ub * blk) {       // the taps of a unit are contiguous in wpack
           tc::mbar_wait(&b_empty[sb], phb ^ 1);
           if (tc::elect_one_sync()) {
-            tc::mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
-            tc::bulk_g2s(sB + sb * B_BYTES, src, B_BYTES, &b_full[sb]);
+            tc::mbar_arrive_expect_tx(&b_full[sb], (uint32_t)p.ub * B_BYTES);
+            tc::bulk_g2s(sB + (size_t)sb * p.ub * B_BYTES, src, (uint32_t)p.ub * B_BYTES, &b_full[sb]);
           }
           __syncwarp();
-          if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+          if (++sb == nsu) { sb = 0; phb ^= 1; }
         }
         it_next(p, it);
       }
@@ -649,6 +651,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t idesc_f2 = tc::make_idesc_bf16(128, 2 * p.BN, 0, 0);
       const uint64_t bdesc_hi_f = tc::make_smem_desc(0, 2u * lbo_b, sbo_b), kstep_b_f = (uint64_t)((4u * lbo_b) >> 4);
       TT_DECL(t_acc); TT_DECL(t_afull); TT_DECL(t_bfull); TT_DECL(t_mma); TT_DECL(n_st);
+      // ONE elected lane runs the whole role (waits included).  Nothing the issuing thread executes overlaps with the MMAs it
+      // has issued -- an mbarrier wait or a tcgen05.commit costs the tensor pipe ~60 idle cycles each, an elect + warp
+      // re-convergence per filter tap ~10 cycles per MMA (scripts/micro/mma_rate2.cu) -- so the loop is MMAs back to back with
+      // one wait (+ fence) + one commit per weight unit (3-4 taps) and one per stage.
+      const int nsu = p.nsb / p.ub;
+      if (tc::elect_one_sync()) {
       while (!it.done) {
         TT_BEGIN;
         if (it.seq != cur_seq) {                            // first stage of a new tile: claim an accumulator buffer
@@ -665,26 +673,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc::mbar_wait(&a_full[sa], pha);
         tc::tc_fence_after();
         TT_ADD(t_afull);
-        // The issuing thread is a single serial instruction stream sharing its scheduler with producer warps: keep it
-        // to a handful of instructions per MMA.  Descriptors differ only in the 14-bit start-address field (16-byte
-        // units, < 2^14 for 227 KB of shared memory), so they are advanced by integer adds on the low word.
+        // Descriptors differ only in the 14-bit start-address field (16-byte units, < 2^14 for 227 KB of shared memory), so
+        // they are advanced by integer adds on the low word.
         const uint64_t a_desc0 = adesc_hi | (uint64_t)((tc::smem_u32(sA + sa * A_BYTES) >> 4) & 0x3FFF);
         uint32_t tap_units = 0;                              // (th * PW + tw) in 16-byte units
-        int twc = 0;
+        int twc = 0, tu = 0;
         for (int t2 = 0; t2 < taps_hw; ++t2) {
-          tc::mbar_wait(&b_full[sb], phb);
-          tc::tc_fence_after();
-          TT_ADD(t_bfull);
+          if (tu == 0) {
+            tc::mbar_wait(&b_full[sb], phb);
+            tc::tc_fence_after();
+            TT_ADD(t_bfull);
+          }
           const uint64_t ad = a_desc0 + (uint64_t)(tap_units * pixu);
-          const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
-          if (tc::elect_one_sync()) {
+          const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + ((size_t)sb * p.ub + tu) * B_BYTES) >> 4) & 0x3FFF);
           if (!p.split) {
             tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
             if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
             if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
             if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
           } else if (FOLD) {
-            const uint64_t bdf = bdesc_hi_f | (uint64_t)((tc::smem_u32(sB + sb * B_BYTES) >> 4) & 0x3FFF);
+            const uint64_t bdf = bdesc_hi_f | (uint64_t)((tc::smem_u32(sB + ((size_t)sb * p.ub + tu) * B_BYTES) >> 4) & 0x3FFF);
             for (int s = 0; s < nk; ++s) {
               const uint64_t ah = ad + (uint64_t)s * kstep_a, bf = bdf + (uint64_t)s * kstep_b_f;
               tc::umma_bf16(tmem_d, ah, bf, idesc_f2, acc);            // A_hi x [B_hi | B_lo] -> columns [0, 2BN)
@@ -698,14 +706,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc_lh, acc);
               tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc_hl, 1u);
               tc::umma_bf16(tmem_d, ah, bh, idesc, 1u);
-              acc = 1;                                   // (elected lane's copy; every lane sets it after the tap)
+              acc = 1;
             }
           }
-          tc::umma_commit(&b_empty[sb]);
-          }
-          __syncwarp();
           acc = 1;
-          if (++sb == p.nsb) { sb = 0; phb ^= 1; }
+          if (++tu == p.ub) {                               // unit consumed: one commit releases its ring slot
+            tu = 0;
+            tc::umma_commit(&b_empty[sb]);
+            if (++sb == nsu) { sb = 0; phb ^= 1; }
+          }
           if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;
           TT_ADD(t_mma);
         }
@@ -713,21 +722,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int sa_done = sa;
         if (++sa == nsa) { sa = 0; pha ^= 1; }
         it_next(p, it);
-        if (tc::elect_one_sync()) {
-          tc::umma_commit(&a_empty[sa_done]);
-          if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
-        }
-        __syncwarp();
+        tc::umma_commit(&a_empty[sa_done]);
+        if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
         TT_ADD(t_mma);
 #ifdef HDN_TC_TIMING
         ++n_st;
 #endif
       }
 #ifdef HDN_TC_TIMING
-      if (blockIdx.x == 0 && lane == 0)
+      if (blockIdx.x == 0)
         printf("[mma] stages %lld  acc_empty %lld  a_full %lld  b_full %lld  issue %lld (cycles/stage)\n", n_st, t_acc / n_st, t_afull / n_st,
                t_bfull / n_st, t_mma / n_st);
 #endif
+      }
+      __syncwarp();
     }
   } else {
     // =================================================================== epilogue (warps 10-13)
@@ -1359,6 +1367,7 @@ struct TcPlan {
   long long op_elems;               // bf16 elements of one pre-packed operand tensor (head; the tail doubles it)
   int fold;
   int BN, n_tiles, KB, CK, nsb, nraw, tmem_cols, flat, PH, PW, P, Ppad, tiles_w, tiles_h;
+  int ub;
   int PHs[2], PWs[2], Ps[2], raw_off[2], ab_off[2], raw_bytes, tab_src[2], tab_vq[2], tab_ints;
   long long ws_elems;
   size_t smem;
@@ -1425,6 +1434,17 @@ TcGeom tc_geom(const hdn_conv* c, int mode) {
   return g;
 }
 
+// Weight ring in units of `ub` filter taps: the issuing thread pays ~60 cycles for every mbarrier wait and every
+// tcgen05.commit, and nothing it executes overlaps with the MMAs it has issued (scripts/micro/mma_rate2.cu: 48 cycles per
+// isolated M=128 x N=64 MMA, 78 with one wait + one commit per 6 MMAs) -- so one barrier pair covers 3-4 taps, not one.
+static void tc_weight_units(TcPlan& pl, int taps_hw) {
+  int ub = 1;
+  for (int u = 4; u >= 2; --u)
+    if (taps_hw % u == 0 && pl.nsb >= 2 * u) { ub = u; break; }
+  pl.ub = ub;
+  pl.nsb = pl.nsb / ub * ub;
+}
+
 TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   TcPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -1482,6 +1502,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
     long long room = budget - (long long)fix - (long long)nsa * (long long)a_bytes;
     int nsb = (int)(room / (long long)b_bytes);
     pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
+    tc_weight_units(pl, g.kh * g.kw);
     pl.nraw = (room >= 2 * (long long)b_bytes) ? nsa : 0;      // reported in the plan's ring-depth slot; 0 = does not fit (narrower tile)
     pl.smem = fix + (size_t)nsa * a_bytes + (size_t)pl.nsb * b_bytes;
     // one operand tensor: K channels per pixel, or -- SWIZZLE_128B form of bf16x3 -- [head 32 | tail 32] per 32-channel group
@@ -1500,6 +1521,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   long long room = budget - (long long)base - (long long)pl.nraw * pl.raw_bytes;
   int nsb = (int)(room / (long long)b_bytes);
   pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
+  tc_weight_units(pl, g.kh * g.kw);
   const size_t fixed = base + pl.nsb * b_bytes;
   pl.smem = fixed + (size_t)pl.nraw * pl.raw_bytes;
   return pl;
@@ -1600,7 +1622,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
   p.pd_lo = g.pd_lo; p.ph_lo = g.ph_lo; p.pw_lo = g.pw_lo;
   p.s2d = g.s2d; p.s2d_quads = g.quads; p.scatter = g.scatter;
   p.K = g.K; p.NC = g.NC;
-  p.BN = pl.BN; p.KB = pl.KB; p.CK = pl.CK; p.nsb = pl.nsb; p.nraw = pl.nraw; p.tmem_cols = pl.tmem_cols;
+  p.BN = pl.BN; p.KB = pl.KB; p.CK = pl.CK; p.nsb = pl.nsb; p.ub = pl.ub; p.nraw = pl.nraw; p.tmem_cols = pl.tmem_cols;
   p.flat = pl.flat; p.PH = pl.PH; p.PW = pl.PW; p.P = pl.P; p.Ppad = pl.Ppad;
   for (int s = 0; s < 2; ++s) {
     p.PHs[s] = pl.PHs[s]; p.PWs[s] = pl.PWs[s]; p.Ps[s] = pl.Ps[s]; p.raw_off[s] = pl.raw_off[s]; p.ab_off[s] = pl.ab_off[s];

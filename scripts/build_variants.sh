@@ -1,7 +1,6 @@
 #!/bin/bash
 # A/B builds of libhdn.so (selected at run time with HDN_LIB=<path>): compile-time variants of conv_tc.cu, and the kernel files
-# of an earlier commit inside today's library, so that two forms can be timed side by side on ONE box (box-to-box spread
-# of the same binary is a few per cent, as large as the effects under study).
+# of an earlier commit inside today's library, so that two forms can be timed side by side in one GPU call.
 #   scripts/build_variants.sh <name> [nvcc -D flags...]            e.g.  nofold -DHDN_NO_FOLD
 #   scripts/build_variants.sh <name> @<commit>                     conv_tc.cu / conv_tc2_wgrad.cu / tc_common.cuh of <commit>
 set -e

@@ -609,10 +609,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t phb = 0;
       const size_t blk = (size_t)p.BN * p.CK * (p.split ? 2 : 1);
       const int nsu = p.nsb / p.ub;                         // ring depth in units
+      TT_DECL(tl_wait); TT_DECL(tl_n);
       while (!it.done) {
         const __nv_bfloat16* src = p.wpack + (((size_t)it.t.n_tile * p.KB + it.kb) * T + (size_t)it.dz * taps_hw) * blk;
         for (int t2 = 0; t2 < taps_hw; t2 += p.ub, src += (size_t)p.ub * blk) {       // the taps of a unit are contiguous in wpack
+          TT_BEGIN;
           tc::mbar_wait(&b_empty[sb], phb ^ 1);
+          TT_ADD(tl_wait);
+#ifdef HDN_TC_TIMING
+          ++tl_n;
+#endif
           if (tc::elect_one_sync()) {
             tc::mbar_arrive_expect_tx(&b_full[sb], (uint32_t)p.ub * B_BYTES);
             tc::bulk_g2s(sB + (size_t)sb * p.ub * B_BYTES, src, (uint32_t)p.ub * B_BYTES, &b_full[sb]);
@@ -622,6 +628,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         it_next(p, it);
       }
+#ifdef HDN_TC_TIMING
+      if (blockIdx.x == 0 && lane == 0) printf("[wld] units %lld  wait-for-empty %lld (cycles/unit)  ub %d nsu %d\n", tl_n, tl_wait / max(tl_n, 1ll), p.ub, nsu);
+#endif
     }
   } else if (warp == 9) {
     // =================================================================== MMA issuer
@@ -651,12 +660,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const uint32_t idesc_f2 = tc::make_idesc_bf16(128, 2 * p.BN, 0, 0);
       const uint64_t bdesc_hi_f = tc::make_smem_desc(0, 2u * lbo_b, sbo_b), kstep_b_f = (uint64_t)((4u * lbo_b) >> 4);
       TT_DECL(t_acc); TT_DECL(t_afull); TT_DECL(t_bfull); TT_DECL(t_mma); TT_DECL(n_st);
-      // ONE elected lane runs the whole role (waits included).  Nothing the issuing thread executes overlaps with the MMAs it
-      // has issued -- an mbarrier wait or a tcgen05.commit costs the tensor pipe ~60 idle cycles each, an elect + warp
-      // re-convergence per filter tap ~10 cycles per MMA (scripts/micro/mma_rate2.cu) -- so the loop is MMAs back to back with
-      // one wait (+ fence) + one commit per weight unit (3-4 taps) and one per stage.
+      // All 32 lanes run the loop converged (waits, iterators, descriptor arithmetic: warp-uniform values that live in uniform
+      // registers); the MMAs of a whole weight unit (3-4 taps) and its commit are issued inside ONE elect_one_sync region.
+      // Nothing the issuing thread executes overlaps with the MMAs it has issued -- an mbarrier wait or a tcgen05.commit costs
+      // the tensor pipe ~60 idle cycles each, an elect + re-convergence ~60 (scripts/micro/mma_rate2.cu) -- so those are paid
+      // per unit, not per tap.  A unit is one filter row (ub == kw): consecutive taps are one pixel apart in the patch.
       const int nsu = p.nsb / p.ub;
-      if (tc::elect_one_sync()) {
+      const uint32_t bstep = B_BYTES >> 4;                   // weight blocks of a unit are B_BYTES apart
+      // the MMAs of one tap (nk K steps; bf16, folded bf16x3 or bf16x3)
+      auto issue_tap = [&](uint64_t ad, uint64_t bd, uint64_t bdf, int nk, uint32_t acc0) {
+        if (!p.split) {
+          tc::umma_bf16(tmem_d, ad, bd, idesc, acc0);
+          if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
+          if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
+          if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
+        } else if (FOLD) {
+          uint32_t a2 = acc0;
+          for (int s = 0; s < nk; ++s) {
+            const uint64_t ah = ad + (uint64_t)s * kstep_a, bf = bdf + (uint64_t)s * kstep_b_f;
+            tc::umma_bf16(tmem_d, ah, bf, idesc_f2, a2);             // A_hi x [B_hi | B_lo] -> columns [0, 2BN)
+            tc::umma_bf16(tmem_d, ah + tail_a, bf, idesc, 1u);       // A_lo x B_hi         -> columns [0, BN)
+            a2 = 1;
+          }
+        } else {
+          // bf16x3: tails first (small terms), head x head last; tail operands sit CK/8 chunks behind the heads
+          uint32_t a2 = acc0;
+          for (int s = 0; s < nk; ++s) {
+            const uint64_t ah = ad + (uint64_t)s * kstep_a, bh = bd + (uint64_t)s * kstep_b;
+            tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc_lh, a2);
+            tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc_hl, 1u);
+            tc::umma_bf16(tmem_d, ah, bh, idesc, 1u);
+            a2 = 1;
+          }
+        }
+      };
       while (!it.done) {
         TT_BEGIN;
         if (it.seq != cur_seq) {                            // first stage of a new tile: claim an accumulator buffer
@@ -677,65 +714,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // they are advanced by integer adds on the low word.
         const uint64_t a_desc0 = adesc_hi | (uint64_t)((tc::smem_u32(sA + sa * A_BYTES) >> 4) & 0x3FFF);
         uint32_t tap_units = 0;                              // (th * PW + tw) in 16-byte units
-        int twc = 0, tu = 0;
-        for (int t2 = 0; t2 < taps_hw; ++t2) {
-          if (tu == 0) {
-            tc::mbar_wait(&b_full[sb], phb);
-            tc::tc_fence_after();
-            TT_ADD(t_bfull);
-          }
+        int twc = 0;
+        for (int t2 = 0; t2 < taps_hw; t2 += p.ub) {
+          tc::mbar_wait(&b_full[sb], phb);
+          tc::tc_fence_after();
+          TT_ADD(t_bfull);
+          const uint32_t sbu = (tc::smem_u32(sB + (size_t)sb * p.ub * B_BYTES) >> 4) & 0x3FFF;
           const uint64_t ad = a_desc0 + (uint64_t)(tap_units * pixu);
-          const uint64_t bd = bdesc_hi | (uint64_t)((tc::smem_u32(sB + ((size_t)sb * p.ub + tu) * B_BYTES) >> 4) & 0x3FFF);
-          if (!p.split) {
-            tc::umma_bf16(tmem_d, ad, bd, idesc, acc);
-            if (nk > 1) tc::umma_bf16(tmem_d, ad + kstep_a, bd + kstep_b, idesc, 1u);
-            if (nk > 2) tc::umma_bf16(tmem_d, ad + 2 * kstep_a, bd + 2 * kstep_b, idesc, 1u);
-            if (nk > 3) tc::umma_bf16(tmem_d, ad + 3 * kstep_a, bd + 3 * kstep_b, idesc, 1u);
-          } else if (FOLD) {
-            const uint64_t bdf = bdesc_hi_f | (uint64_t)((tc::smem_u32(sB + ((size_t)sb * p.ub + tu) * B_BYTES) >> 4) & 0x3FFF);
-            for (int s = 0; s < nk; ++s) {
-              const uint64_t ah = ad + (uint64_t)s * kstep_a, bf = bdf + (uint64_t)s * kstep_b_f;
-              tc::umma_bf16(tmem_d, ah, bf, idesc_f2, acc);            // A_hi x [B_hi | B_lo] -> columns [0, 2BN)
-              tc::umma_bf16(tmem_d, ah + tail_a, bf, idesc, 1u);       // A_lo x B_hi         -> columns [0, BN)
-              acc = 1;
-            }
-          } else {
-            // bf16x3: tails first (small terms), head x head last; tail operands sit CK/8 chunks behind the heads
-            for (int s = 0; s < nk; ++s) {
-              const uint64_t ah = ad + (uint64_t)s * kstep_a, bh = bd + (uint64_t)s * kstep_b;
-              tc::umma_bf16(tmem_d, ah + tail_a, bh, idesc_lh, acc);
-              tc::umma_bf16(tmem_d, ah, bh + tail_b, idesc_hl, 1u);
-              tc::umma_bf16(tmem_d, ah, bh, idesc, 1u);
-              acc = 1;
-            }
+          const uint64_t bd = bdesc_hi | (uint64_t)sbu, bdf = bdesc_hi_f | (uint64_t)sbu;
+          if (tc::elect_one_sync()) {
+            issue_tap(ad, bd, bdf, nk, acc);
+            if (p.ub > 1) issue_tap(ad + pixu, bd + bstep, bdf + bstep, nk, 1u);
+            if (p.ub > 2) issue_tap(ad + 2 * pixu, bd + 2 * bstep, bdf + 2 * bstep, nk, 1u);
+            if (p.ub > 3) issue_tap(ad + 3 * pixu, bd + 3 * bstep, bdf + 3 * bstep, nk, 1u);
+            tc::umma_commit(&b_empty[sb]);                 // unit consumed: one commit releases its ring slot
           }
+          __syncwarp();
           acc = 1;
-          if (++tu == p.ub) {                               // unit consumed: one commit releases its ring slot
-            tu = 0;
-            tc::umma_commit(&b_empty[sb]);
-            if (++sb == nsu) { sb = 0; phb ^= 1; }
-          }
-          if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;
+          if (++sb == nsu) { sb = 0; phb ^= 1; }
+          if (p.ub == p.kw) tap_units += (uint32_t)p.PW;       // next filter row
+          else if (++twc == p.kw) { twc = 0; tap_units += (uint32_t)(p.PW - p.kw + 1); } else ++tap_units;   // single-tap units
           TT_ADD(t_mma);
         }
         const int seq_before = it.seq;
         const int sa_done = sa;
         if (++sa == nsa) { sa = 0; pha ^= 1; }
         it_next(p, it);
-        tc::umma_commit(&a_empty[sa_done]);
-        if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
+        if (tc::elect_one_sync()) {
+          tc::umma_commit(&a_empty[sa_done]);
+          if (it.done || it.seq != seq_before) tc::umma_commit(&acc_full[seq_before & 1]);   // tile finished
+        }
+        __syncwarp();
         TT_ADD(t_mma);
 #ifdef HDN_TC_TIMING
         ++n_st;
 #endif
       }
 #ifdef HDN_TC_TIMING
-      if (blockIdx.x == 0)
+      if (blockIdx.x == 0 && lane == 0)
         printf("[mma] stages %lld  acc_empty %lld  a_full %lld  b_full %lld  issue %lld (cycles/stage)\n", n_st, t_acc / n_st, t_afull / n_st,
                t_bfull / n_st, t_mma / n_st);
 #endif
-      }
-      __syncwarp();
     }
   } else {
     // =================================================================== epilogue (warps 10-13)
@@ -1437,12 +1456,9 @@ TcGeom tc_geom(const hdn_conv* c, int mode) {
 // Weight ring in units of `ub` filter taps: the issuing thread pays ~60 cycles for every mbarrier wait and every
 // tcgen05.commit, and nothing it executes overlaps with the MMAs it has issued (scripts/micro/mma_rate2.cu: 48 cycles per
 // isolated M=128 x N=64 MMA, 78 with one wait + one commit per 6 MMAs) -- so one barrier pair covers 3-4 taps, not one.
-static void tc_weight_units(TcPlan& pl, int taps_hw) {
-  int ub = 1;
-  for (int u = 4; u >= 2; --u)
-    if (taps_hw % u == 0 && pl.nsb >= 2 * u) { ub = u; break; }
-  pl.ub = ub;
-  pl.nsb = pl.nsb / ub * ub;
+static void tc_weight_units(TcPlan& pl, int kw) {       // a unit is one filter row (ub == kw) or one tap
+  pl.ub = (kw >= 2 && kw <= 4 && pl.nsb >= 2 * kw) ? kw : 1;
+  pl.nsb = pl.nsb / pl.ub * pl.ub;
 }
 
 TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
@@ -1502,7 +1518,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
     long long room = budget - (long long)fix - (long long)nsa * (long long)a_bytes;
     int nsb = (int)(room / (long long)b_bytes);
     pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
-    tc_weight_units(pl, g.kh * g.kw);
+    tc_weight_units(pl, g.kw);
     pl.nraw = (room >= 2 * (long long)b_bytes) ? nsa : 0;      // reported in the plan's ring-depth slot; 0 = does not fit (narrower tile)
     pl.smem = fix + (size_t)nsa * a_bytes + (size_t)pl.nsb * b_bytes;
     // one operand tensor: K channels per pixel, or -- SWIZZLE_128B form of bf16x3 -- [head 32 | tail 32] per 32-channel group
@@ -1521,7 +1537,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   long long room = budget - (long long)base - (long long)pl.nraw * pl.raw_bytes;
   int nsb = (int)(room / (long long)b_bytes);
   pl.nsb = nsb < 2 ? 2 : (nsb > NSB_MAX ? NSB_MAX : nsb);
-  tc_weight_units(pl, g.kh * g.kw);
+  tc_weight_units(pl, g.kw);
   const size_t fixed = base + pl.nsb * b_bytes;
   pl.smem = fixed + (size_t)pl.nraw * pl.raw_bytes;
   return pl;

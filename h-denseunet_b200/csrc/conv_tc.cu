@@ -200,7 +200,7 @@ __device__ __forceinline__ void cp_async_wait(int n) {     // n groups may remai
   }
 }
 __device__ __forceinline__ void bar_producers() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
-__device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 3, 128;" ::: "memory"); }
+template <int NT> __device__ __forceinline__ void bar_epilogue() { asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory"); }
 
 // Regroup the two channel quads a lane holds ([4*l8, +4) and [32 + 4*l8, +4)) with its neighbour lane into
 // 8-channel chunks and store the 16-byte chunk of pixel q.
@@ -226,6 +226,12 @@ template <int MODE, bool FOLD, int OPER>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr bool TMA = OPER != 0;
   constexpr bool SW = OPER == 2;
+  // In the TMA forms one lane of warp 0 feeds the A ring and warps 1-7 have nothing to do: warps 4-7 join the epilogue as a
+  // second set (same TMEM lane quarters, the odd 32-column blocks), which doubles the loads / reductions the epilogue keeps
+  // in flight -- the data-gradient epilogues and the 1x1 forward epilogue bound their kernels (profiles/r02r_role_timing.txt).
+  constexpr int NEW = TMA ? 8 : 4;                          // epilogue warps
+  constexpr int NET = NEW * 32;
+  constexpr int NSET = NEW / 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the 128-byte swizzle is a function of the shared-memory address bits 4-9: stages start on 1024-byte boundaries
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   float* sstat = reinterpret_cast<float*>(tabs + NTAB * p.tab_ints);        // [2 buffers][4][BN]
   double* dstat = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(sstat + 8 * p.BN) + 7) & ~uintptr_t(7));   // [4][BN] per-CTA sums
   uint8_t* sEpi = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dstat + 4 * p.BN) + 15) & ~uintptr_t(15));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + 4 * EPI_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + NEW * EPI_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + MAXNSA;
   uint64_t* b_full = a_empty + MAXNSA;
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (tid == 0) {
     for (int i = 0; i < MAXNSA; ++i) { tc::mbar_init(&a_full[i], TMA ? 1 : NPROD); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NSB_MAX; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], NET); }
     tc::fence_barrier_init();
   }
   if (warp == 9) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
@@ -265,8 +271,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int taps_hw = p.kh * p.kw;
   const int T = p.kd * taps_hw;
 
-  if (warp < 8) {
-    // =================================================================== A producers
+  if (warp < (TMA ? 4 : 8)) {
+    // =================================================================== A producers (TMA forms: warp 0 alone)
     const int ptid = tid;                                 // 0..255
     const int l8 = lane & 7, pg = lane >> 3;
     int built_seq = -1;
@@ -758,8 +764,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else {
     // =================================================================== epilogue (warps 10-13)
-    const int etid = tid - 320;                             // 0..127
-    uint8_t* escr = sEpi + (size_t)(warp - 10) * EPI_BYTES;  // this warp's transpose tile + row-offset tables
+    const int eset = warp >= 10 ? 0 : 1;                    // warps 10-13: set 0; (TMA forms) warps 4-7: set 1
+    const int ew = warp >= 10 ? warp - 10 : warp;           // 0..3 / 4..7
+    const int etid = ew * 32 + lane;                        // 0..NET-1
+    uint8_t* escr = sEpi + (size_t)ew * EPI_BYTES;          // this warp's transpose tile + row-offset tables
     float* tT = reinterpret_cast<float*>(escr);             // [32][33]
     long long* ro0 = reinterpret_cast<long long*>(escr + 32 * 33 * 4);   // [32]  output row offsets (fprop)
     long long* rox = ro0;                                    // [2][32] stored-value row offsets (dgrad)
@@ -776,11 +784,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // column owned by one epilogue thread, and reach global memory ONCE per CTA and column tile: a double atomic per tile
     // and column from 148 CTAs onto the same few addresses serialises in L2 (16 384 tiles x 128 atomics for the 64-wide
     // decoder tail) and throttled the whole pipeline.
-    for (int i = etid; i < 4 * p.BN; i += 128) dstat[i] = 0.0;
+    for (int i = etid; i < 4 * p.BN; i += NET) dstat[i] = 0.0;
     int flush_ntile = -1;
     auto flush_stats = [&](int nt) {
       if (MODE == 0) {
-        for (int c = etid; c < p.BN; c += 128) {
+        for (int c = etid; c < p.BN; c += NET) {
           const int col = nt * p.BN + c;
           if (col < p.NC) { atomicAdd(p.stat_sum + col, dstat[c]); atomicAdd(p.stat_sq + col, dstat[p.BN + c]); }
           dstat[c] = 0.0; dstat[p.BN + c] = 0.0;
@@ -789,7 +797,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int e = 0; e < p.nepi; ++e) {
           const hdn_dgrad_epi& E = p.epi[e];
           if (E.mode == 2 || E.s1 == nullptr) continue;
-          for (int c = etid; c < p.BN; c += 128) {
+          for (int c = etid; c < p.BN; c += NET) {
             const int col = nt * p.BN + c;
             const double s1 = dstat[(2 * e) * p.BN + c], s2 = dstat[(2 * e + 1) * p.BN + c];
             if (col < p.NC) {
@@ -823,8 +831,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       else if (!p.scatter)
         for (int e = 0; e < p.nepi; ++e) any_s = any_s || (p.epi[e].mode != 2 && p.epi[e].s1 != nullptr);
       if (any_s) {
-        for (int i = etid; i < 4 * p.BN; i += 128) st_[i] = 0.f;
-        bar_epilogue();
+        for (int i = etid; i < 4 * p.BN; i += NET) st_[i] = 0.f;
+        bar_epilogue<NET>();
       }
 #ifdef HDN_TC_TIMING
       long long te0 = clock64();
@@ -859,7 +867,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         rod[lane] = m;                                      // linear position (dropout hash index)
         const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
         __syncwarp();
-        for (int cb = 0; cb < p.BN; cb += 32) {
+        for (int cb = eset * 32; cb < p.BN; cb += 32 * NSET) {
           const int ncols = min(32, p.BN - cb);
           float v2[16];
           ld_acc(cb, v);
@@ -950,8 +958,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[ab]);                   // accumulator buffer may be overwritten
         if (do_stats) {
-          bar_epilogue();
-          for (int c = etid; c < p.BN; c += 128) { dstat[c] += (double)st_[c]; dstat[p.BN + c] += (double)st_[p.BN + c]; }
+          bar_epilogue<NET>();
+          for (int c = etid; c < p.BN; c += NET) { dstat[c] += (double)st_[c]; dstat[p.BN + c] += (double)st_[p.BN + c]; }
           flush_ntile = n_tile;
         }
       } else if (p.scatter) {
@@ -1000,7 +1008,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         const unsigned vmask = __ballot_sync(0xffffffffu, rvalid);
         __syncwarp();
-        if (p.epi_pf) {
+        if (p.epi_pf && eset == 0) {
           // The stored values this epilogue reads were written a whole forward pass ago: they come from DRAM, and the few
           // 16-byte loads a lane keeps in flight make the epilogue latency-bound.  Pull the NEXT tile's rows into L2 now
           // (one row per thread, a prefetch per 128-byte line): by the time that tile's accumulator is ready they are L2 hits.
@@ -1027,7 +1035,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
           }
         }
-        for (int cb = 0; cb < p.BN; cb += 32) {
+        for (int cb = eset * 32; cb < p.BN; cb += 32 * NSET) {
           const int ncols = min(32, p.BN - cb);
           float v2[16];
           ld_acc(cb, v);
@@ -1129,11 +1137,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         tc::tc_fence_before();
         tc::mbar_arrive(&acc_empty[ab]);
         if (any_s) {
-          bar_epilogue();
+          bar_epilogue<NET>();
           for (int e = 0; e < p.nepi; ++e) {
             const hdn_dgrad_epi& E = p.epi[e];
             if (E.mode == 2 || E.s1 == nullptr) continue;
-            for (int c = etid; c < p.BN; c += 128) {
+            for (int c = etid; c < p.BN; c += NET) {
               dstat[(2 * e) * p.BN + c] += (double)st_[(2 * e) * p.BN + c];
               dstat[(2 * e + 1) * p.BN + c] += (double)st_[(2 * e + 1) * p.BN + c];
             }
@@ -1510,7 +1518,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   if (pl.tma) {
     // no raw ring, no geometry tables: the A ring gets up to 4 stages next to >= taps_hw (<= 12) weight blocks
     pl.tab_ints = 0; pl.raw_bytes = 0;
-    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 4ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128 + 1024;
+    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 8ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128 + 1024;
     const int want_b = g.kh * g.kw < 4 ? 4 : (g.kh * g.kw > 12 ? 12 : g.kh * g.kw);
     int nsa = 4;
     while (nsa > 2 && (long long)(fix + nsa * a_bytes + (size_t)want_b * b_bytes) > budget) --nsa;

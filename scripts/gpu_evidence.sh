@@ -22,12 +22,11 @@ cap fianl_conv wgrad 1 conv_wgrad_tc2_kernel 2 wgrad_tc2_fianl_conv
 cap fianl_conv wgrad 1 act_pack_bf16_kernel 4 act_pack_fianl_conv
 cap dense2_x1 dgrad 2 conv_tc_kernel 2 dgrad_x3_dense2_x1 src
 cap dense2_x1 fprop 2 conv_tc_kernel 2 fprop_x3_dense2_x1 src
-cap dense2_x1 wgrad 1 conv_wgrad_tc2_kernel 2 wgrad_tc2_dense2_x1
 cap dense2_x2 fprop 2 conv_tc_kernel 2 fprop_x3_dense2_x2
 # (3) the other kernels inside a real (reduced-batch: 1 slab x 16 slices) step: speed-of-light + memory sections
 timeout 1200 $NCU --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy \
    -k regex:'pool|bn_|wce_|sgd_|dropout|triplets|cat4|colstats|colsum|zero_window|pack_weights|small_n|conv_wgrad_tc_kernel' \
-   -f -o gpurun_out/r02_ncu_elementwise python scripts/one_step.py 1 16 512 > gpurun_out/r02_ncu_elementwise.log 2>&1
+   -c 120 -f -o gpurun_out/r02_ncu_elementwise python scripts/one_step.py 1 16 512 > gpurun_out/r02_ncu_elementwise.log 2>&1
 ncu -i gpurun_out/r02_ncu_elementwise.ncu-rep --page raw --csv > gpurun_out/r02_ncu_elementwise.raw.csv 2>> gpurun_out/r02_ncu_elementwise.log
 rm -f gpurun_out/r02_ncu_elementwise.ncu-rep
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/r02_evidence_clocks.txt

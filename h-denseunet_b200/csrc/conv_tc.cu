@@ -62,7 +62,8 @@ constexpr bool kFpropQuad = false;
 constexpr bool kFpropQuad = true;
 #endif
 
-constexpr int TC_THREADS = 448;   // warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
+constexpr int TC_THREADS = 448;   // SIMT-producer form: warps 0-7 producers, 8 weight loader, 9 MMA issuer, 10-13 epilogue
+constexpr int TC_THREADS_TMA = 512;   // TMA forms: warp 0 tile loads, 1 weight loader, 2 MMA issuer, (3 idle,) 4-15 three epilogue sets
 constexpr int NPROD = 256;        // producer threads
 constexpr int NSA = 2;        // bf16 A-operand stages of the SIMT-producer form
 constexpr int MAXNSA = 6;     // ... upper bound (TMA mode: TcParams::nsa stages)
@@ -223,15 +224,17 @@ __device__ __forceinline__ void store_chunks(uint8_t* dst, uint32_t ppad, int q,
 // every launch the 3x3(x3) layers ran 7 % slower (profiles/r02n_variants.txt: one box, five builds side by side).
 //   MODE 0 fprop, 1 dgrad;  FOLD: TcParams::fold;  OPER 0 SIMT producers (stems), 1 TMA chunk planes, 2 TMA 128-byte swizzled rows
 template <int MODE, bool FOLD, int OPER>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(OPER ? TC_THREADS_TMA : TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr bool TMA = OPER != 0;
   constexpr bool SW = OPER == 2;
-  // In the TMA forms one lane of warp 0 feeds the A ring and warps 1-7 have nothing to do: warps 4-7 join the epilogue as a
-  // second set (same TMEM lane quarters, the odd 32-column blocks), which doubles the loads / reductions the epilogue keeps
-  // in flight -- the data-gradient epilogues and the 1x1 forward epilogue bound their kernels (profiles/r02r_role_timing.txt).
-  constexpr int NEW = TMA ? 8 : 4;                          // epilogue warps
+  // In the TMA forms one lane of warp 0 feeds the A ring and the eight transform warps of the SIMT form are not needed: the
+  // CTA has 16 warps, twelve of them epilogue warps in three sets (same TMEM lane quarters, 32-column blocks taken round
+  // robin), which triples the loads / reductions the epilogue keeps in flight -- the data-gradient epilogues and the 1x1
+  // forward epilogue bound their kernels (profiles/r02r_role_timing.txt; 4 -> 8 warps: dense2_x1 dgrad 1.78 -> 1.17 ms).
+  constexpr int NEW = TMA ? 12 : 4;                         // epilogue warps
   constexpr int NET = NEW * 32;
   constexpr int NSET = NEW / 4;
+  constexpr int W_LOAD = TMA ? 1 : 8, W_MMA = TMA ? 2 : 9, W_EPI0 = TMA ? 4 : 10;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // the 128-byte swizzle is a function of the shared-memory address bits 4-9: stages start on 1024-byte boundaries
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], NET); }
     tc::fence_barrier_init();
   }
-  if (warp == 9) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (warp == W_MMA) tc::tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int taps_hw = p.kh * p.kw;
   const int T = p.kd * taps_hw;
 
-  if (warp < (TMA ? 4 : 8)) {
+  if (warp < (TMA ? 1 : 8)) {
     // =================================================================== A producers (TMA forms: warp 0 alone)
     const int ptid = tid;                                 // 0..255
     const int l8 = lane & 7, pg = lane >> 3;
@@ -605,7 +608,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         it_next(p, tr);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == W_LOAD) {
     // =================================================================== weight loader (TMA engine)
     // all 32 lanes run the loop converged; one elected lane issues (see tc::elect_one_sync)
     {
@@ -638,7 +641,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (blockIdx.x == 0 && lane == 0) printf("[wld] units %lld  wait-for-empty %lld (cycles/unit)  ub %d nsu %d\n", tl_n, tl_wait / max(tl_n, 1ll), p.ub, nsu);
 #endif
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // =================================================================== MMA issuer
     // all 32 lanes run the loop converged (waits, iterators); the tcgen05.mma / commit issue sits under elect_one_sync
     {
@@ -762,10 +765,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                t_bfull / n_st, t_mma / n_st);
 #endif
     }
-  } else {
-    // =================================================================== epilogue (warps 10-13)
-    const int eset = warp >= 10 ? 0 : 1;                    // warps 10-13: set 0; (TMA forms) warps 4-7: set 1
-    const int ew = warp >= 10 ? warp - 10 : warp;           // 0..3 / 4..7
+  } else if (warp >= W_EPI0) {
+    // =================================================================== epilogue (warps 10-13, or 4-15 in the TMA forms)
+    const int ew = warp - W_EPI0;                           // 0..NEW-1
+    const int eset = ew >> 2;                               // set s takes the 32-column blocks s, s + NSET, ...
     const int etid = ew * 32 + lane;                        // 0..NET-1
     uint8_t* escr = sEpi + (size_t)ew * EPI_BYTES;          // this warp's transpose tile + row-offset tables
     float* tT = reinterpret_cast<float*>(escr);             // [32][33]
@@ -1162,7 +1165,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   // ---- teardown
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc::tc_fence_after();
     tc::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -1518,7 +1521,7 @@ TcPlan tc_plan1(const hdn_conv* c, const TcGeom& g, int mode, int extra_tiles) {
   if (pl.tma) {
     // no raw ring, no geometry tables: the A ring gets up to 4 stages next to >= taps_hw (<= 12) weight blocks
     pl.tab_ints = 0; pl.raw_bytes = 0;
-    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 8ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128 + 1024;
+    const size_t fix = 8ull * pl.BN * 4 + 32ull * pl.BN + 8 + 16 + 12ull * EPI_BYTES + (2 * MAXNSA + 2 * NSB_MAX + 4) * 8 + 16 + 128 + 1024;
     const int want_b = g.kh * g.kw < 4 ? 4 : (g.kh * g.kw > 12 ? 12 : g.kh * g.kw);
     int nsa = 4;
     while (nsa > 2 && (long long)(fix + nsa * a_bytes + (size_t)want_b * b_bytes) > budget) --nsa;
@@ -1566,7 +1569,7 @@ int tc_run(unsigned grid, size_t smem, cudaStream_t st, const TcParams& p) {
     if (e != cudaSuccess) { hdn_set_error("conv tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
     attr_set = true;
   }
-  conv_tc_kernel<MODE, FOLD, OPER><<<grid, TC_THREADS, smem, st>>>(p);
+  conv_tc_kernel<MODE, FOLD, OPER><<<grid, OPER ? TC_THREADS_TMA : TC_THREADS, smem, st>>>(p);
   return HDN_OK;
 }
 int tc_dispatch(int mode, int fold, int oper, unsigned grid, size_t smem, cudaStream_t st, const TcParams& p) {

@@ -1336,13 +1336,13 @@ int hdn_tc_fastx() {
   return v;
 }
 
-// HDN_TC_X3FOLD=1: folded bf16x3 (A_hi x [B_hi | B_lo] as one MMA of N = 2*BN, + A_lo x B_hi): 2 MMAs and 14 KB of
+// HDN_TC_X3FOLD (default 1): folded bf16x3 (A_hi x [B_hi | B_lo] as one MMA of N = 2*BN, + A_lo x B_hi): 2 MMAs and 14 KB of
 // shared-memory operand reads per K step instead of 3 MMAs and 18 KB (BN = 64); see TcParams::fold.  Also hdn_set_switch().
 static int g_tc_x3fold = -1;
 int hdn_tc_x3fold() {
   if (g_tc_x3fold < 0) {
     const char* e = getenv("HDN_TC_X3FOLD");
-    g_tc_x3fold = (e && atoi(e) != 0) ? 1 : 0;
+    g_tc_x3fold = (e && atoi(e) == 0) ? 0 : 1;            // default on: forward launches 3-6 % faster, data gradients equal (profiles/r02u_*)
   }
   return g_tc_x3fold;
 }

@@ -22,7 +22,7 @@
  *       HDN_POOL_FAST=0|1   vector max-pool backward (default 1)
  *       HDN_TC_L2PF=0|1     L2::256B prefetch hint on the raw patch copies (default 0, experiment)
  *       HDN_TC_X3FOLD=0|1   folded bf16x3 issue scheme: A_hi x [B_hi | B_lo] as one MMA of N = 2*BN plus A_lo x B_hi
- *                           (2 MMAs per K step instead of 3; layers with BN <= 128); also hdn_set_switch()
+ *                           (2 MMAs per K step instead of 3; layers with BN <= 128; default 1); also hdn_set_switch()
  *       HDN_TC_TMA=0|1|2    fprop / dgrad operand path: bf16 pre-pass + TMA tile loads for no layer / the 3x3(x3) layers /
  *                           all stride-1 layers (default 2); also hdn_set_switch()
  *       HDN_TC_SW128=0|1    TMA mode with 128-byte swizzled K-major operand rows instead of 16-byte chunk planes

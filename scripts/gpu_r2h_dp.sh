@@ -4,7 +4,6 @@
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511"
 timeout 600 $TR scripts/dp_check.py > gpurun_out/r2h_dp_check_flags.txt 2>&1
-HDN_DP_SYNC=host timeout 600 $TR scripts/dp_check.py > gpurun_out/r2h_dp_check_host.txt 2>&1
 timeout 900 $TR bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu > gpurun_out/r2h_bench_c4_2gpu.json 2> gpurun_out/r2h_bench_c4_2gpu_err.txt
-timeout 1200 $TR bench.py --gpus 2 --config c5 --depth 256 --steps 1 --warmup 3 --no-cpu > gpurun_out/r2h_bench_c5_2gpu_z256.json 2> gpurun_out/r2h_bench_c5_2gpu_err.txt
+timeout 1200 $TR bench.py --gpus 2 --config c5 --depth 128 --steps 1 --warmup 3 --no-cpu > gpurun_out/r2h_bench_c5_2gpu_z128.json 2> gpurun_out/r2h_bench_c5_2gpu_err.txt
 echo done > gpurun_out/r2h_status.txt

@@ -335,13 +335,14 @@ def test_fprop_dgrad_tma_swizzle128(cuda_dev, name, prec):
         _switch("HDN_TC_SW128", 0)
 
 
+@pytest.mark.parametrize("fold", [0, 1], ids=["three_mma", "folded"])
 @pytest.mark.parametrize("name", TMA_CASES)
-def test_fprop_dgrad_x3_folded(cuda_dev, name):
-    """HDN_TC_X3FOLD=1: bf16x3 as two MMAs per K step -- A_hi x [B_hi | B_lo] with N = 2*BN into a double-width accumulator
-    (the halves are added when the epilogue reads TMEM) and A_lo x B_hi."""
+def test_fprop_dgrad_x3_forms(cuda_dev, name, fold):
+    """Both issue schemes of bf16x3.  HDN_TC_X3FOLD=1 (default): two MMAs per K step -- A_hi x [B_hi | B_lo] with N = 2*BN into a
+    double-width accumulator (the halves are added when the epilogue reads TMEM) and A_lo x B_hi; 0: three MMAs."""
     kw = dict(CASES[name])
     kw.setdefault("fold", tuple(True for _ in kw.get("ups", ((1, 1, 1),))))
-    _switch("HDN_TC_X3FOLD", 1)
+    _switch("HDN_TC_X3FOLD", fold)
     try:
         c = Case(cuda_dev, tc=2, **kw)
         TOL = TOLS[2]
@@ -359,4 +360,4 @@ def test_fprop_dgrad_x3_folded(cuda_dev, name):
                     assert rel_l2(g1, g0) < TOL, (name, mode, acc, rel_l2(g1, g0))
                     assert rel_l2(S1[0], S0[0]) < TOL and rel_l2(S1[1], S0[1]) < TOL
     finally:
-        _switch("HDN_TC_X3FOLD", 0)
+        _switch("HDN_TC_X3FOLD", 1)

@@ -33,6 +33,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, the default of some launchers) goes there too
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 

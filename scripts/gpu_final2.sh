@@ -10,5 +10,6 @@ for cfg in c2 c3; do
   timeout 600 python bench.py --config $cfg --steps 5 --warmup 3 > gpurun_out/r02_bench_$cfg.json 2> gpurun_out/r02_bench_${cfg}_err.txt; cut -c1-200 gpurun_out/r02_bench_$cfg.json
 done
 timeout 900 python bench.py --config c5 --steps 1 --warmup 3 --no-cpu > gpurun_out/r02_bench_c5.json 2> gpurun_out/r02_bench_c5_err.txt; cut -c1-200 gpurun_out/r02_bench_c5.json
+timeout 120 scripts/micro/mma_rate 148 quick > gpurun_out/r02_mma_rate_mn.txt 2>&1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r02_final_clocks.txt
 du -sk gpurun_out > gpurun_out/r02_final_status.txt

@@ -18,7 +18,7 @@ __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64
       : "memory");
 }
 
-struct Args { int N, layout, ts, shift, R, nbuf; };
+struct Args { int N, layout, ts, shift, R, nbuf, mn; };   // mn: both operands MN-major (the weight-gradient kernel's form)
 
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -35,14 +35,17 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a, long long* out
   tc::tc_fence_after();
   const uint32_t tm = tbase;
   if (warp == 0) {
-    const uint32_t idesc = tc::make_idesc_bf16(128, a.N, 0, 0);
+    const uint32_t idesc = tc::make_idesc_bf16(128, a.N, a.mn, a.mn);
     const uint32_t sA = tc::smem_u32(smem), sB = tc::smem_u32(smem + 96 * 1024);
     const uint64_t sw_bit = (uint64_t)2 << 61;
     // layout 0: K-major chunk planes, A plane = 180 px * 16 B (patch-like), B plane = N * 16 B;  layout 2: 128-byte swizzled rows
-    const uint64_t ad0 = a.layout ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, 184u * 16u, 128u);
-    const uint64_t bd0 = a.layout ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, (uint32_t)a.N * 16u, 128u);
-    const uint32_t a_stride = a.layout ? 16384u : 8192u;     // bytes between the rotating A buffers
-    const uint32_t b_stride = a.layout ? (uint32_t)a.N * 128u : (uint32_t)a.N * 64u;
+    // MN-major, no swizzle: core matrix = 8 K rows x 16 B (8 MN elements), K groups 128 B apart (LBO), MN groups 2 KB apart (SBO)
+    const uint64_t ad0 = a.mn ? tc::make_smem_desc(0, 128u, 2048u)
+                              : a.layout ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, 184u * 16u, 128u);
+    const uint64_t bd0 = a.mn ? tc::make_smem_desc(0, 128u, 2048u)
+                              : a.layout ? (tc::make_smem_desc(0, 16u, 1024u) | sw_bit) : tc::make_smem_desc(0, (uint32_t)a.N * 16u, 128u);
+    const uint32_t a_stride = a.mn ? 0u : a.layout ? 16384u : 8192u;     // bytes between the rotating A buffers
+    const uint32_t b_stride = a.mn ? 0u : a.layout ? (uint32_t)a.N * 128u : (uint32_t)a.N * 64u;
     long long t0 = 0, t1 = 0;
     for (int pass = 0; pass < 2; ++pass) {                   // pass 0 warms up
       __syncwarp();
@@ -88,6 +91,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(Args a, long long* out
 int main(int argc, char** argv) {
   const int grid = argc > 1 ? atoi(argv[1]) : 148;
   const int R = 4096;
+  const bool quick = argc > 2;                              // second argument: only the base rows + the MN-major rows
   long long* d;
   cudaMalloc(&d, 1024 * sizeof(long long));
   cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -99,7 +103,8 @@ int main(int argc, char** argv) {
         for (int nbuf = 1; nbuf <= 4; nbuf += 3)
           for (int N : Ns) {
             if (ts && (layout || shift)) continue;
-            Args a{N, layout, ts, shift, R, nbuf};
+            if (quick && (layout || nbuf > 1 || shift)) continue;
+            Args a{N, layout, ts, shift, R, nbuf, 0};
             mma_rate_kernel<<<grid, 128, 200 * 1024>>>(a, d);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("N=%d layout=%d ts=%d: %s\n", N, layout, ts, cudaGetErrorString(e)); return 1; }
@@ -110,5 +115,18 @@ int main(int argc, char** argv) {
                    nbuf, N, (double)h[0] / R, (double)h[grid / 2] / R, (double)h[grid - 1] / R, N / 2);
             fflush(stdout);
           }
+  for (int shift = 0; shift < 2; ++shift)
+    for (int N : Ns) {
+      Args a{N, 0, 0, shift, R, 1, 1};
+      mma_rate_kernel<<<grid, 128, 200 * 1024>>>(a, d);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("MN-major N=%d: %s\n", N, cudaGetErrorString(e)); return 1; }
+      std::vector<long long> h(grid);
+      cudaMemcpy(h.data(), d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+      std::sort(h.begin(), h.end());
+      printf("A=smem MN-major (both operands) shift=%d N=%3d : %7.1f / %7.1f / %7.1f   (floor %d)\n", shift, N, (double)h[0] / R, (double)h[grid / 2] / R,
+             (double)h[grid - 1] / R, N / 2);
+      fflush(stdout);
+    }
   return 0;
 }

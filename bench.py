@@ -33,9 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, the default of some launchers) goes there too
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries ONE JSON line: NCCL writes its version banner (any NCCL_DEBUG level >= VERSION) to stdout unless told otherwise
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -387,10 +386,11 @@ def run_gpu(a):
     m.train_on_batch(x, y)
     for _ in range(max(a.warmup - 1, 0)):
         m.train_step_device(net)
-    l0 = net.be.launches
+    l0, k0 = net.be.launches, net.be.lib.hdn_launch_count()
     with ClockSampler(local) as clk:
         ms, loss = timed(lambda: m.train_step_device(net), a.steps, dist, dev)
-    launches = (net.be.launches - l0) // a.steps
+    calls = (net.be.launches - l0) // a.steps               # C-ABI calls per step
+    launches = net.be.lib.hdn_launch_count() - k0           # kernels libhdn launched inside the timed region (all steps)
     clocks = clk.summary()
 
     # end-to-end arm: the call the reference scripts make (train_hybrid.py:213, train_2ddense.py:209): fit_generator over a
@@ -423,7 +423,7 @@ def run_gpu(a):
                                "every step"},
         "e2e": {"value": e2e, "unit": cfg["unit"], "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 16},
-        "gpu_launches": int(launches), "clocks": clocks, "loss": loss, "memory_gib": net.memory_bytes() / 2 ** 30,
+        "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(a.steps, 1), "cabi_calls_per_step": int(calls), "clocks": clocks, "loss": loss, "memory_gib": net.memory_bytes() / 2 ** 30,
     }
 
     # roofline of the dominant kernel class, measured live with CUDA events (one extra instrumented step; every rank
@@ -505,10 +505,13 @@ def run_c5(a):
         st = {}
         for _ in range(max(a.warmup // 3, 1) if a.steps else 0):            # one untimed volume (programs, staging, clocks)
             hdn.predict_tumor_inwindow(m, imgs, 3, mini, maxi, args, reuse_2d=reuse, stats=st)
+        from h_denseunet_b200 import _lib as _hl
+        k0 = _hl.load().hdn_launch_count()
         t0 = time.perf_counter()
         with ClockSampler(local) as clk:
             ms, res = timed(lambda: hdn.predict_tumor_inwindow(m, imgs, 3, mini, maxi, args, reuse_2d=reuse, stats=st), a.steps, dist, dev)
         wall = (time.perf_counter() - t0) / max(a.steps, 1)
+        klaunch = int(_hl.load().hdn_launch_count() - k0)
         nwin = len(starts)
         naive = nwin * fwd_tflop
         dedup = naive - (nwin * a.cols - st["slices_2d"] * world) * f2d if reuse else naive
@@ -516,7 +519,7 @@ def run_c5(a):
                       "windows_this_rank": st["windows"], "slices_2d_this_rank": st["slices_2d"],
                       "tflop_naive": round(naive, 1), "tflop_evaluated": round(dedup, 1),
                       "tflops_naive_rate": round(naive / (ms * 1e-3), 1), "clocks": clk.summary(),
-                      "checksum": [float(res[0].sum()), float(res[1].sum())]}
+                      "checksum": [float(res[0].sum()), float(res[1].sum())], "gpu_launches": klaunch}
     if rank == 0:
         best = out[True] if out[True]["s_per_volume"] < out[False]["s_per_volume"] else out[False]
         line = {"metric": cfg["metric"], "value": best["volumes_per_s"], "unit": cfg["unit"], "n_gpus": world, "steps": a.steps,
@@ -530,7 +533,7 @@ def run_c5(a):
                         "h2d_bytes_per_step": int(len(starts) / world * a.size * a.size * a.cols * 4),
                         "d2h_bytes_per_step": int(a.size * a.size * Z * 2 * 4)},
                 "without_slice_reuse": out[False], "with_slice_reuse": out[True],
-                "gpu_launches": None, "clocks": best["clocks"]}
+                "gpu_launches": best["gpu_launches"], "clocks": best["clocks"]}
         sustained = peaks.get("bf16_tflops_sustained") or 1400.0
         line["roofline"] = {"kernel": "whole window forward (231 convolutions)", "bound": "tensor", "achieved": best["tflops_naive_rate"] / world,
                             "peak": sustained, "unit": "TFLOP/s", "frac": best["tflops_naive_rate"] / world / sustained, "traffic": None,

@@ -96,7 +96,7 @@ class Aug(C.Structure):
 
 
 EXPORTS = [
-    "hdn_last_error", "hdn_version", "hdn_conv_fprop", "hdn_conv_dgrad", "hdn_conv_wgrad",
+    "hdn_last_error", "hdn_version", "hdn_launch_count", "hdn_conv_fprop", "hdn_conv_dgrad", "hdn_conv_wgrad",
     "hdn_conv_tc_supported", "hdn_conv_tc_workspace", "hdn_conv_tc_plan", "hdn_pool_fwd", "hdn_pool_bwd", "hdn_bn_fold", "hdn_bn_param_grad",
     "hdn_bn_bwd_apply", "hdn_dropout_bwd", "hdn_col_stats", "hdn_wce_accum", "hdn_wce_grad",
     "hdn_triplets", "hdn_cat4", "hdn_cat4_bwd", "hdn_sgd_nesterov", "hdn_dp_reduce_sgd",
@@ -122,6 +122,7 @@ def load():
                        "there is no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     lib.hdn_last_error.restype = C.c_char_p
+    lib.hdn_launch_count.restype = C.c_longlong
     vp, i32, i64, f32, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
     sig = {
         "hdn_conv_fprop": [C.POINTER(Conv), vp],

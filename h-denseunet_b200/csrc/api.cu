@@ -51,6 +51,9 @@ extern "C" int64_t hdn_conv_tc_workspace(const hdn_conv* c, int pass) {
   return (int64_t)hdn_tc_workspace_bytes(c, pass);
 }
 
+thread_local long long hdn_tl_launches = 0;
+extern "C" long long hdn_launch_count(void) { return hdn_tl_launches; }
+
 // Process-wide switches (the environment variables of the same name set the defaults, see the top of hdn.h).
 extern "C" int hdn_set_switch(const char* name, int value) {
   HDN_CHECK_ARG(name != nullptr, "set_switch: null name");

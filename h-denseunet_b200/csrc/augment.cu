@@ -136,9 +136,9 @@ extern "C" int hdn_aug_sample(const hdn_aug* a, float* x, float* y, int32_t* cou
   HDN_CHECK_ARG(y == nullptr || (a->ys0 >= 0 && a->yns > 0 && a->ys0 + a->yns <= a->cs), "aug_sample: label slices outside the crop");
   cudaStream_t st = (cudaStream_t)stream;
   int* mm = reinterpret_cast<int*>(scratch);
-  aug_init_kernel<<<1, 1, 0, st>>>(mm);
-  aug_minmax_kernel<<<agrid((int64_t)a->ch * a->cw * a->cs), AT, 0, st>>>(*a, mm);
-  aug_sample_kernel<<<agrid((int64_t)a->cs * a->out_h * a->out_w), AT, 0, st>>>(*a, x, y, counts, mm);
+  HDN_LAUNCHED(1), aug_init_kernel<<<1, 1, 0, st>>>(mm);
+  HDN_LAUNCHED(1), aug_minmax_kernel<<<agrid((int64_t)a->ch * a->cw * a->cs), AT, 0, st>>>(*a, mm);
+  HDN_LAUNCHED(1), aug_sample_kernel<<<agrid((int64_t)a->cs * a->out_h * a->out_w), AT, 0, st>>>(*a, x, y, counts, mm);
   HDN_CHECK_LAUNCH("aug_sample");
   return HDN_OK;
 }

@@ -532,7 +532,7 @@ extern "C" int hdn_col_stats(hdn_tensor y, int64_t M, int C, double* sum, double
   HDN_CHECK_ARG(y.p && sum && sq && M > 0 && C > 0, "col_stats: bad arguments");
   int64_t rpb = 1024;
   dim3 grid((unsigned)hdn_cdiv(M, rpb), (unsigned)hdn_cdiv(C, 32));
-  colstats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, M, C, sum, sq, rpb);
+  HDN_LAUNCHED(1), colstats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, M, C, sum, sq, rpb);
   HDN_CHECK_LAUNCH("col_stats");
   return HDN_OK;
 }
@@ -569,7 +569,7 @@ int hdn_validate_conv(const hdn_conv* c) {
 int hdn_conv_fprop_simt(const hdn_conv* c, cudaStream_t st) {
   const int64_t M = (int64_t)c->N * c->D * c->H * c->W;
   dim3 grid((unsigned)hdn_cdiv(M, BM), (unsigned)hdn_cdiv(c->Cout, BN));
-  conv_fprop_simt<<<grid, NT, 0, st>>>(*c, M);
+  HDN_LAUNCHED(1), conv_fprop_simt<<<grid, NT, 0, st>>>(*c, M);
   HDN_CHECK_LAUNCH("conv_fprop_simt");
   return HDN_OK;
 }
@@ -581,7 +581,7 @@ int hdn_conv_dgrad_simt(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_
     const int nq = c->Cin / 4, lanes = 256 / nq;
     int64_t blocks = hdn_cdiv(M, (int64_t)lanes * 4 * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    conv_dgrad_small_n4<4><<<(unsigned)blocks, 256, 0, st>>>(*c, epi[0], M, nq);
+    HDN_LAUNCHED(1), conv_dgrad_small_n4<4><<<(unsigned)blocks, 256, 0, st>>>(*c, epi[0], M, nq);
     HDN_CHECK_LAUNCH("conv_dgrad_small_n4");
     return HDN_OK;
   }
@@ -590,7 +590,7 @@ int hdn_conv_dgrad_simt(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_
     const hdn_src& s = c->src[si];
     const int64_t Ms = (int64_t)c->N * s.D * s.H * s.W;
     dim3 grid((unsigned)hdn_cdiv(Ms, BM), (unsigned)hdn_cdiv(c->Cin, BN));
-    conv_dgrad_simt<<<grid, NT, 0, st>>>(*c, epi[si], si, Ms);
+    HDN_LAUNCHED(1), conv_dgrad_simt<<<grid, NT, 0, st>>>(*c, epi[si], si, Ms);
     HDN_CHECK_LAUNCH("conv_dgrad_simt");
   }
   return HDN_OK;
@@ -599,7 +599,7 @@ int hdn_conv_dgrad_simt(const hdn_conv* c, const hdn_dgrad_epi* epi, cudaStream_
 int hdn_colsum(hdn_tensor y, int64_t M, int C, float* out, cudaStream_t st) {
   int64_t rpb = 4096;
   dim3 grid((unsigned)hdn_cdiv(M, rpb), (unsigned)hdn_cdiv(C, 32));
-  colsum_kernel<<<grid, 256, 0, st>>>(y, M, C, out, rpb);
+  HDN_LAUNCHED(1), colsum_kernel<<<grid, 256, 0, st>>>(y, M, C, out, rpb);
   HDN_CHECK_LAUNCH("colsum");
   return HDN_OK;
 }
@@ -610,7 +610,7 @@ int hdn_conv_wgrad_simt(const hdn_conv* c, float* dw, cudaStream_t st) {
     const int nq = c->Cin / 4, lanes = 256 / nq;
     int64_t blocks = hdn_cdiv(M, (int64_t)lanes * 4 * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    conv_wgrad_small_n4<4><<<(unsigned)blocks, 256, 0, st>>>(*c, dw, M, nq);
+    HDN_LAUNCHED(1), conv_wgrad_small_n4<4><<<(unsigned)blocks, 256, 0, st>>>(*c, dw, M, nq);
     HDN_CHECK_LAUNCH("conv_wgrad_small_n4");
     return HDN_OK;
   }
@@ -619,7 +619,7 @@ int hdn_conv_wgrad_simt(const hdn_conv* c, float* dw, cudaStream_t st) {
     const int lanes = 256 / c->Cin;
     int64_t blocks = hdn_cdiv(M, (int64_t)lanes * 64);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    conv_wgrad_small_n<<<(unsigned)blocks, 256, 0, st>>>(*c, dw, M, lanes);
+    HDN_LAUNCHED(1), conv_wgrad_small_n<<<(unsigned)blocks, 256, 0, st>>>(*c, dw, M, lanes);
     HDN_CHECK_LAUNCH("conv_wgrad_small_n");
     return HDN_OK;
   }
@@ -634,7 +634,7 @@ int hdn_conv_wgrad_simt(const hdn_conv* c, float* dw, cudaStream_t st) {
   splits = hdn_cdiv(M, rps);
   if (splits > 65535) { rps = hdn_cdiv(hdn_cdiv(M, 65535), BK) * BK; splits = hdn_cdiv(M, rps); }
   dim3 grid((unsigned)tiles, (unsigned)splits, (unsigned)taps);
-  conv_wgrad_simt<<<grid, NT, 0, st>>>(*c, dw, M, rps);
+  HDN_LAUNCHED(1), conv_wgrad_simt<<<grid, NT, 0, st>>>(*c, dw, M, rps);
   HDN_CHECK_LAUNCH("conv_wgrad_simt");
   return HDN_OK;
 }

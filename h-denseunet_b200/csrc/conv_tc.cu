@@ -1569,7 +1569,7 @@ int tc_run(unsigned grid, size_t smem, cudaStream_t st, const TcParams& p) {
     if (e != cudaSuccess) { hdn_set_error("conv tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
     attr_set = true;
   }
-  conv_tc_kernel<MODE, FOLD, OPER><<<grid, OPER ? TC_THREADS_TMA : TC_THREADS, smem, st>>>(p);
+  HDN_LAUNCHED(1), conv_tc_kernel<MODE, FOLD, OPER><<<grid, OPER ? TC_THREADS_TMA : TC_THREADS, smem, st>>>(p);
   return HDN_OK;
 }
 int tc_dispatch(int mode, int fold, int oper, unsigned grid, size_t smem, cudaStream_t st, const TcParams& p) {
@@ -1608,11 +1608,11 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
     long long total = pl.ws_elems / 8;
     unsigned gr = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
     if (pl.sw)
-      pack_weights_sw_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, mode, nsplit == 2 ? 1 : 0, total);
+      HDN_LAUNCHED(1), pack_weights_sw_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, mode, nsplit == 2 ? 1 : 0, total);
     else if (g.s2d || g.scatter)
-      pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
+      HDN_LAUNCHED(1), pack_weights_s2d_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, g.quads == 8 ? 1 : 0, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
     else
-      pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
+      HDN_LAUNCHED(1), pack_weights_kernel<<<gr, 256, 0, st>>>(c->w, wp, c->Cin, c->Cout, c->kd, c->kh, c->kw, pl.BN, pl.KB, pl.CK, mode, nsplit, pl.fold, tail16, total);
     HDN_CHECK_LAUNCH("pack_weights");
   }
   TcParams p;
@@ -1694,7 +1694,7 @@ int tc_launch(const hdn_conv* c, const hdn_dgrad_epi* epi, int mode, cudaStream_
         const long long Ms = (long long)c->N * s.D * s.H * s.W;
         if (epi[i].mode == 0) {
           unsigned gr = (unsigned)((Ms * c->Cin + 255) / 256 > 148 * 16 ? 148 * 16 : (Ms * c->Cin + 255) / 256);
-          zero_window_kernel<<<gr, 256, 0, st>>>(epi[i].dx, Ms, c->Cin);
+          HDN_LAUNCHED(1), zero_window_kernel<<<gr, 256, 0, st>>>(epi[i].dx, Ms, c->Cin);
           HDN_CHECK_LAUNCH("zero_window");
         } else {
           cudaError_t e = cudaMemsetAsync(epi[i].du, 0, (size_t)Ms * c->Cin * sizeof(float), st);

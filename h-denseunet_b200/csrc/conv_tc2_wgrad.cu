@@ -465,7 +465,7 @@ int pack_launch(const hdn_src* srcs, int nsrc, int N, int D, int H, int W, int C
   pp.total = (long long)N * D * H * W * (interleave ? (C + 31) / 32 * 4 : C / 8);
   const long long blocks = (pp.total + 255) / 256;
   const unsigned grid = (unsigned)(blocks > 148 * 32 ? 148 * 32 : blocks);
-  act_pack_bf16_kernel<<<grid, 256, 0, st>>>(pp);
+  HDN_LAUNCHED(1), act_pack_bf16_kernel<<<grid, 256, 0, st>>>(pp);
   HDN_CHECK_LAUNCH("act_pack_bf16");
   return HDN_OK;
 }
@@ -575,7 +575,7 @@ int hdn_conv_wgrad_tc2(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.dw = dw; p.tmem_cols = pl.tmem_cols;
   HDN_CHECK_ARG(pl.n_pos_tiles < (1ll << 31), "conv_wgrad tc2: too many position tiles");
   dim3 grid((unsigned)(pl.ci_tiles * pl.co_tiles * pl.groups), (unsigned)pl.splits);
-  conv_wgrad_tc2_kernel<<<grid, W2_THREADS, pl.smem, st>>>(p);
+  HDN_LAUNCHED(1), conv_wgrad_tc2_kernel<<<grid, W2_THREADS, pl.smem, st>>>(p);
   HDN_CHECK_LAUNCH("conv_wgrad_tc2");
   return HDN_OK;
 }

@@ -859,7 +859,7 @@ int hdn_conv_wgrad_tc(const hdn_conv* c, float* dw, cudaStream_t st) {
   p.tab_dy = pl.tab_dy; p.tab_ints = pl.tab_ints;
   HDN_CHECK_ARG(pl.n_pos_tiles < (1ll << 31), "conv_wgrad tc: too many position tiles");
   dim3 grid((unsigned)(pl.ci_tiles * pl.co_tiles * pl.groups), (unsigned)pl.splits);
-  conv_wgrad_tc_kernel<<<grid, WG_THREADS, pl.smem, st>>>(p);
+  HDN_LAUNCHED(1), conv_wgrad_tc_kernel<<<grid, WG_THREADS, pl.smem, st>>>(p);
   HDN_CHECK_LAUNCH("conv_wgrad_tc");
   return HDN_OK;
 }

@@ -559,8 +559,8 @@ extern "C" int hdn_pool_fwd(const hdn_pool* p, void* stream) {
   HDN_CHECK_ARG(p && p->src.t.p && p->y.p, "pool_fwd: null pointer");
   HDN_CHECK_ARG(p->kind == 0 || p->kind == 1, "pool: kind must be 0 (max) or 1 (avg)");
   const int64_t total = (int64_t)p->N * p->D * p->H * p->W * p->C;
-  if (p->kind == 0) maxpool_fwd<<<grid_for(total), ET, 0, ST>>>(*p, total);
-  else avgpool_fwd<<<grid_for(total), ET, 0, ST>>>(*p, total);
+  if (p->kind == 0) HDN_LAUNCHED(1), maxpool_fwd<<<grid_for(total), ET, 0, ST>>>(*p, total);
+  else HDN_LAUNCHED(1), avgpool_fwd<<<grid_for(total), ET, 0, ST>>>(*p, total);
   HDN_CHECK_LAUNCH("pool_fwd");
   return HDN_OK;
 }
@@ -581,10 +581,10 @@ extern "C" int hdn_pool_bwd(const hdn_pool* p, const hdn_dgrad_epi* e, void* str
     const unsigned ppb = ET / (unsigned)(p->C / 4);
     int64_t blocks = hdn_cdiv(M_in, (int64_t)ppb);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    maxpool_bwd_idx_v4<<<(unsigned)blocks, ET, sm, ST>>>(*p, *e, (unsigned)M_in);
-  } else if (p->kind == 0 && p->argidx) maxpool_bwd_idx<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
-  else if (p->kind == 0) maxpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
-  else avgpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
+    HDN_LAUNCHED(1), maxpool_bwd_idx_v4<<<(unsigned)blocks, ET, sm, ST>>>(*p, *e, (unsigned)M_in);
+  } else if (p->kind == 0 && p->argidx) HDN_LAUNCHED(1), maxpool_bwd_idx<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
+  else if (p->kind == 0) HDN_LAUNCHED(1), maxpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
+  else HDN_LAUNCHED(1), avgpool_bwd<<<grid_for(total), ET, sm, ST>>>(*p, *e, total);
   HDN_CHECK_LAUNCH("pool_bwd");
   return HDN_OK;
 }
@@ -592,26 +592,26 @@ extern "C" int hdn_bn_fold(const hdn_bn_fold_t* f, void* stream) {
   HDN_CHECK_ARG(f && f->C > 0 && f->a && f->b, "bn_fold: bad descriptor");
   HDN_CHECK_ARG(f->mode == 0 || (f->sum && f->sumsq && f->count > 0), "bn_fold: training mode needs statistics");
   HDN_CHECK_ARG(f->mode == 1 || (f->mov_mean && f->mov_var), "bn_fold: inference mode needs moving statistics");
-  bn_fold_kernel<<<(unsigned)hdn_cdiv(f->C, 128), 128, 0, ST>>>(*f);
+  HDN_LAUNCHED(1), bn_fold_kernel<<<(unsigned)hdn_cdiv(f->C, 128), 128, 0, ST>>>(*f);
   HDN_CHECK_LAUNCH("bn_fold");
   return HDN_OK;
 }
 extern "C" int hdn_bn_param_grad(const hdn_bn_grad_t* g, void* stream) {
   HDN_CHECK_ARG(g && g->C > 0 && g->s1 && g->s2 && g->mean && g->rstd, "bn_param_grad: bad descriptor");
-  bn_param_grad_kernel<<<(unsigned)hdn_cdiv(g->C, 128), 128, 0, ST>>>(*g);
+  HDN_LAUNCHED(1), bn_param_grad_kernel<<<(unsigned)hdn_cdiv(g->C, 128), 128, 0, ST>>>(*g);
   HDN_CHECK_LAUNCH("bn_param_grad");
   return HDN_OK;
 }
 extern "C" int hdn_bn_bwd_apply(const float* du, hdn_tensor x, hdn_tensor dx, int64_t M, int C, const float* k0,
                                 const float* k1, const float* k2, const float* mean, int accumulate, void* stream) {
   HDN_CHECK_ARG(du && x.p && dx.p && k0 && k1 && k2 && mean && M > 0 && C > 0, "bn_bwd_apply: bad arguments");
-  bn_bwd_apply_kernel<<<grid_for(M * C, 4), ET, 0, ST>>>(du, x, dx, M * C, C, k0, k1, k2, mean, accumulate);
+  HDN_LAUNCHED(1), bn_bwd_apply_kernel<<<grid_for(M * C, 4), ET, 0, ST>>>(du, x, dx, M * C, C, k0, k1, k2, mean, accumulate);
   HDN_CHECK_LAUNCH("bn_bwd_apply");
   return HDN_OK;
 }
 extern "C" int hdn_dropout_bwd(hdn_tensor g, int64_t M, int C, float keep, uint64_t seed, void* stream) {
   HDN_CHECK_ARG(g.p && M > 0 && C > 0 && keep > 0.f && keep <= 1.f, "dropout_bwd: bad arguments");
-  dropout_bwd_kernel<<<grid_for(M * C, 4), ET, 0, ST>>>(g, M * C, C, keep, seed);
+  HDN_LAUNCHED(1), dropout_bwd_kernel<<<grid_for(M * C, 4), ET, 0, ST>>>(g, M * C, C, keep, seed);
   HDN_CHECK_LAUNCH("dropout_bwd");
   return HDN_OK;
 }
@@ -619,7 +619,7 @@ extern "C" int hdn_wce_accum(const float* logits, const float* labels, int64_t N
                              double* acc, void* stream) {
   HDN_CHECK_ARG(logits && labels && acc && N > 0 && D > 0 && HW > 0, "wce_accum: bad arguments");
   const int64_t total = N * D * HW;
-  wce_accum_kernel<<<grid_for(total, 4), ET, 0, ST>>>(logits, labels, total, D, HW, d0, d1, acc);
+  HDN_LAUNCHED(1), wce_accum_kernel<<<grid_for(total, 4), ET, 0, ST>>>(logits, labels, total, D, HW, d0, d1, acc);
   HDN_CHECK_LAUNCH("wce_accum");
   return HDN_OK;
 }
@@ -627,32 +627,32 @@ extern "C" int hdn_wce_grad(const float* logits, const float* labels, float* dlo
                             int d0, int d1, const double* acc, float gscale, void* stream) {
   HDN_CHECK_ARG(logits && labels && dlogits && acc, "wce_grad: null pointer");
   const int64_t total = N * D * HW;
-  wce_grad_kernel<<<grid_for(total, 4), ET, 0, ST>>>(logits, labels, dlogits, total, D, HW, d0, d1, acc, gscale);
+  HDN_LAUNCHED(1), wce_grad_kernel<<<grid_for(total, 4), ET, 0, ST>>>(logits, labels, dlogits, total, D, HW, d0, d1, acc, gscale);
   HDN_CHECK_LAUNCH("wce_grad");
   return HDN_OK;
 }
 extern "C" int hdn_triplets(const float* vol, float* out, int B, int S, int64_t HW, int ldc, void* stream) {
   HDN_CHECK_ARG(vol && out && B > 0 && S > 0 && HW > 0 && ldc >= 3, "triplets: bad arguments");
-  triplets_kernel<<<grid_for((int64_t)B * S * HW, 2), ET, 0, ST>>>(vol, out, B, S, HW, ldc);
+  HDN_LAUNCHED(1), triplets_kernel<<<grid_for((int64_t)B * S * HW, 2), ET, 0, ST>>>(vol, out, B, S, HW, ldc);
   HDN_CHECK_LAUNCH("triplets");
   return HDN_OK;
 }
 extern "C" int hdn_cat4(const float* vol, const float* logits, float* out, int64_t M, float k, void* stream) {
   HDN_CHECK_ARG(vol && logits && out && M > 0, "cat4: bad arguments");
-  cat4_kernel<<<grid_for(M, 2), ET, 0, ST>>>(vol, logits, (float4*)out, M, k);
+  HDN_LAUNCHED(1), cat4_kernel<<<grid_for(M, 2), ET, 0, ST>>>(vol, logits, (float4*)out, M, k);
   HDN_CHECK_LAUNCH("cat4");
   return HDN_OK;
 }
 extern "C" int hdn_cat4_bwd(const float* dout, float* dlogits, int64_t M, float k, int accumulate, void* stream) {
   HDN_CHECK_ARG(dout && dlogits && M > 0, "cat4_bwd: bad arguments");
-  cat4_bwd_kernel<<<grid_for(M, 2), ET, 0, ST>>>((const float4*)dout, dlogits, M, k, accumulate);
+  HDN_LAUNCHED(1), cat4_bwd_kernel<<<grid_for(M, 2), ET, 0, ST>>>((const float4*)dout, dlogits, M, k, accumulate);
   HDN_CHECK_LAUNCH("cat4_bwd");
   return HDN_OK;
 }
 extern "C" int hdn_sgd_nesterov(float* p, const float* g, float* m, int64_t n, float lr, float mu, float gscale,
                                 void* stream) {
   HDN_CHECK_ARG(p && g && m && n > 0, "sgd: bad arguments");
-  sgd_kernel<<<grid_for(n, 4), ET, 0, ST>>>(p, g, m, n, lr, mu, gscale);
+  HDN_LAUNCHED(1), sgd_kernel<<<grid_for(n, 4), ET, 0, ST>>>(p, g, m, n, lr, mu, gscale);
   HDN_CHECK_LAUNCH("sgd");
   return HDN_OK;
 }
@@ -664,21 +664,21 @@ extern "C" int hdn_dp_reduce_sgd(float* const* peer_p, const float* const* peer_
   if (hi == lo) return HDN_OK;
   PeerTable t;
   for (int r = 0; r < world; ++r) { t.p[r] = peer_p[r]; t.g[r] = peer_g[r]; }
-  dp_reduce_sgd_kernel<<<grid_for(hi - lo, 8), ET, 0, ST>>>(t, m_local, world, rank, lo, hi, lr, mu, gscale);
+  HDN_LAUNCHED(1), dp_reduce_sgd_kernel<<<grid_for(hi - lo, 8), ET, 0, ST>>>(t, m_local, world, rank, lo, hi, lr, mu, gscale);
   HDN_CHECK_LAUNCH("dp_reduce_sgd");
   return HDN_OK;
 }
 extern "C" int hdn_window_accumulate(const float* logits, float* score, int* count, int S, int64_t HW, int z0,
                                      void* stream) {
   HDN_CHECK_ARG(logits && score && count && S > 2 && S <= 1024 && HW > 0, "window_accumulate: bad arguments");
-  window_acc_kernel<<<grid_for((int64_t)(S - 2) * HW, 2), ET, 0, ST>>>(logits, score, S, HW, z0);
-  window_cnt_kernel<<<1, 1024, 0, ST>>>(count, S, z0);
+  HDN_LAUNCHED(1), window_acc_kernel<<<grid_for((int64_t)(S - 2) * HW, 2), ET, 0, ST>>>(logits, score, S, HW, z0);
+  HDN_LAUNCHED(1), window_cnt_kernel<<<1, 1024, 0, ST>>>(count, S, z0);
   HDN_CHECK_LAUNCH("window_accumulate");
   return HDN_OK;
 }
 extern "C" int hdn_window_finalize(float* score, const int* count, int Z, int64_t HW, void* stream) {
   HDN_CHECK_ARG(score && count && Z > 0 && HW > 0, "window_finalize: bad arguments");
-  window_fin_kernel<<<grid_for((int64_t)Z * HW, 2), ET, 0, ST>>>(score, count, Z, HW);
+  HDN_LAUNCHED(1), window_fin_kernel<<<grid_for((int64_t)Z * HW, 2), ET, 0, ST>>>(score, count, Z, HW);
   HDN_CHECK_LAUNCH("window_finalize");
   return HDN_OK;
 }
@@ -687,21 +687,21 @@ extern "C" int hdn_dp_signal(unsigned int* const* peer_flags, int world, int ran
   HDN_CHECK_ARG(peer_flags && world >= 1 && world <= 16 && rank >= 0 && rank < world, "dp_signal: bad arguments");
   FlagTable t;
   for (int r = 0; r < world; ++r) t.f[r] = peer_flags[r];
-  dp_signal_kernel<<<1, 32, 0, ST>>>(t, world, rank, value);
+  HDN_LAUNCHED(1), dp_signal_kernel<<<1, 32, 0, ST>>>(t, world, rank, value);
   HDN_CHECK_LAUNCH("dp_signal");
   return HDN_OK;
 }
 extern "C" int hdn_dp_wait(const unsigned int* flags, int world, unsigned int value, void* stream) {
   HDN_CHECK_ARG(flags && world >= 1 && world <= 16, "dp_wait: bad arguments");
-  dp_wait_kernel<<<1, 32, 0, ST>>>(flags, world, value);
+  HDN_LAUNCHED(1), dp_wait_kernel<<<1, 32, 0, ST>>>(flags, world, value);
   HDN_CHECK_LAUNCH("dp_wait");
   return HDN_OK;
 }
 extern "C" int hdn_layout_nhws_to_nshw(const void* in, float* out, int N, int H, int W, int S, int is_int16, void* stream) {
   HDN_CHECK_ARG(in && out && N > 0 && H > 0 && W > 0 && S > 0 && (int64_t)N * H < 65536, "layout: bad arguments");
   dim3 grid((unsigned)((W + 31) / 32), (unsigned)((S + 31) / 32), (unsigned)(N * H));
-  if (is_int16) nhws_to_nshw_kernel<short><<<grid, 256, 0, ST>>>(reinterpret_cast<const short*>(in), out, H, W, S);
-  else nhws_to_nshw_kernel<float><<<grid, 256, 0, ST>>>(reinterpret_cast<const float*>(in), out, H, W, S);
+  if (is_int16) HDN_LAUNCHED(1), nhws_to_nshw_kernel<short><<<grid, 256, 0, ST>>>(reinterpret_cast<const short*>(in), out, H, W, S);
+  else HDN_LAUNCHED(1), nhws_to_nshw_kernel<float><<<grid, 256, 0, ST>>>(reinterpret_cast<const float*>(in), out, H, W, S);
   HDN_CHECK_LAUNCH("layout_nhws_to_nshw");
   return HDN_OK;
 }

@@ -7,6 +7,9 @@
 #include "../../include/hdn.h"
 
 void hdn_set_error(const char* fmt, ...);
+// kernels launched by this thread since the library was loaded (hdn_launch_count(); bench.py reports the count of the timed region)
+extern thread_local long long hdn_tl_launches;
+#define HDN_LAUNCHED(n) (hdn_tl_launches += (n))
 
 #define HDN_CHECK_ARG(cond, ...)                          \
   do {                                                    \

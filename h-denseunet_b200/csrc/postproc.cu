@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(PT) and_kernel(const unsigned char* __restrict
 
 int ccl(const unsigned char* in, int* L, int X, int Y, int Z, int conn26, int invert, cudaStream_t st) {
   const int64_t n = (int64_t)X * Y * Z;
-  ccl_init_kernel<<<pgrid(n), PT, 0, st>>>(in, L, n, invert);
-  ccl_merge_kernel<<<pgrid(n), PT, 0, st>>>(L, X, Y, Z, conn26);
-  ccl_compress_kernel<<<pgrid(n), PT, 0, st>>>(L, n);
+  HDN_LAUNCHED(1), ccl_init_kernel<<<pgrid(n), PT, 0, st>>>(in, L, n, invert);
+  HDN_LAUNCHED(1), ccl_merge_kernel<<<pgrid(n), PT, 0, st>>>(L, X, Y, Z, conn26);
+  HDN_LAUNCHED(1), ccl_compress_kernel<<<pgrid(n), PT, 0, st>>>(L, n);
   HDN_CHECK_LAUNCH("post ccl");
   return HDN_OK;
 }
@@ -160,14 +160,14 @@ int ccl(const unsigned char* in, int* L, int X, int Y, int Z, int conn26, int in
 extern "C" int hdn_post_threshold(const float* score_liver, const float* score_tumor, unsigned char* liver, unsigned char* tumor,
                                   int64_t n, float thres_liver, float thres_tumor, void* stream) {
   HDN_CHECK_ARG(score_liver && score_tumor && liver && tumor && n > 0, "post_threshold: bad arguments");
-  threshold_kernel<<<pgrid(n), PT, 0, PST>>>(score_liver, score_tumor, liver, tumor, n, thres_liver, thres_tumor);
+  HDN_LAUNCHED(1), threshold_kernel<<<pgrid(n), PT, 0, PST>>>(score_liver, score_tumor, liver, tumor, n, thres_liver, thres_tumor);
   HDN_CHECK_LAUNCH("post_threshold");
   return HDN_OK;
 }
 
 extern "C" int hdn_post_dilate(const unsigned char* in, unsigned char* out, int X, int Y, int Z, void* stream) {
   HDN_CHECK_ARG(in && out && in != out && POST_ARGS_OK(X, Y, Z), "post_dilate: bad arguments");
-  dilate6_kernel<<<pgrid((int64_t)X * Y * Z), PT, 0, PST>>>(in, out, X, Y, Z);
+  HDN_LAUNCHED(1), dilate6_kernel<<<pgrid((int64_t)X * Y * Z), PT, 0, PST>>>(in, out, X, Y, Z);
   HDN_CHECK_LAUNCH("post_dilate");
   return HDN_OK;
 }
@@ -185,9 +185,9 @@ extern "C" int hdn_post_largest_component(const unsigned char* in, unsigned char
   if (rc) return rc;
   cudaError_t e = cudaMemsetAsync(size, 0, (size_t)n * 4 + 8, PST);
   if (e != cudaSuccess) { hdn_set_error("post_largest_component: memset: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
-  ccl_count_kernel<<<pgrid(n), PT, 0, PST>>>(L, size, n);
-  ccl_argmax_kernel<<<pgrid(n), PT, 0, PST>>>(L, size, n, best);
-  ccl_select_kernel<<<pgrid(n), PT, 0, PST>>>(L, out, n, best);
+  HDN_LAUNCHED(1), ccl_count_kernel<<<pgrid(n), PT, 0, PST>>>(L, size, n);
+  HDN_LAUNCHED(1), ccl_argmax_kernel<<<pgrid(n), PT, 0, PST>>>(L, size, n, best);
+  HDN_LAUNCHED(1), ccl_select_kernel<<<pgrid(n), PT, 0, PST>>>(L, out, n, best);
   HDN_CHECK_LAUNCH("post_largest_component");
   return HDN_OK;
 }
@@ -203,22 +203,22 @@ extern "C" int hdn_post_fill_holes(const unsigned char* in, unsigned char* out, 
   if (rc) return rc;
   cudaError_t e = cudaMemsetAsync(flag, 0, (size_t)n * 4, PST);
   if (e != cudaSuccess) { hdn_set_error("post_fill_holes: memset: %s", cudaGetErrorString(e)); return HDN_ERR_CUDA; }
-  border_mark_kernel<<<pgrid(n), PT, 0, PST>>>(L, flag, X, Y, Z);
-  fill_select_kernel<<<pgrid(n), PT, 0, PST>>>(L, flag, out, n);
+  HDN_LAUNCHED(1), border_mark_kernel<<<pgrid(n), PT, 0, PST>>>(L, flag, X, Y, Z);
+  HDN_LAUNCHED(1), fill_select_kernel<<<pgrid(n), PT, 0, PST>>>(L, flag, out, n);
   HDN_CHECK_LAUNCH("post_fill_holes");
   return HDN_OK;
 }
 
 extern "C" int hdn_post_and(const unsigned char* a, const unsigned char* b, unsigned char* out, int64_t n, void* stream) {
   HDN_CHECK_ARG(a && b && out && n > 0, "post_and: bad arguments");
-  and_kernel<<<pgrid(n), PT, 0, PST>>>(a, b, out, n);
+  HDN_LAUNCHED(1), and_kernel<<<pgrid(n), PT, 0, PST>>>(a, b, out, n);
   HDN_CHECK_LAUNCH("post_and");
   return HDN_OK;
 }
 
 extern "C" int hdn_post_compose(const unsigned char* liver, const unsigned char* tumor, unsigned char* out, int64_t n, void* stream) {
   HDN_CHECK_ARG(liver && tumor && out && n > 0, "post_compose: bad arguments");
-  compose_kernel<<<pgrid(n), PT, 0, PST>>>(liver, tumor, out, n);
+  HDN_LAUNCHED(1), compose_kernel<<<pgrid(n), PT, 0, PST>>>(liver, tumor, out, n);
   HDN_CHECK_LAUNCH("post_compose");
   return HDN_OK;
 }

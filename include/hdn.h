@@ -50,6 +50,8 @@ const char* hdn_last_error(void);
 int hdn_version(void);
 /* Set a process-wide switch by its environment-variable name (tests flip kernels inside one process). */
 int hdn_set_switch(const char* name, int value);
+/* Kernels this thread has launched through the library since it was loaded (every <<<>>> is counted). */
+long long hdn_launch_count(void);
 
 typedef struct {
   const float* p;   /* base pointer (device) */

@@ -249,7 +249,10 @@ def run_reference(a):
         "impl": "reference", "metric": cfg["metric"], "value": v, "unit": cfg["unit"], "n_gpus": a.gpus, "steps": n,
         "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s, CPU sample %dx%dx%s" % (a.config, a.cpu_size, a.cpu_size, a.cpu_cols), "statistic": "median of %d" % n},
+        "config": {"workload": WORKLOAD_TEXT[a.config] % dict(batch=a.batch, size=a.size, cols=a.cols or 0), "baseline_config": a.config,
+                   "shape": [a.size, a.size] + ([a.cols] if a.cols else []), "batch_per_gpu": a.batch, "precision": "fp32 (CPU port of the reference graph)",
+                   "sample": "each step = one %dx%dx%s sample of that workload on the host cores, scaled by voxel count" % (a.cpu_size, a.cpu_size, a.cpu_cols),
+                   "statistic": "median of %d" % n},
         "cpu_baseline": {"value": v, "unit": cfg["unit"], "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": cfg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "loss": out}))

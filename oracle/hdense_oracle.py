@@ -321,8 +321,9 @@ def forward_2d(params, x_nhwc, training=False, learn_bn=True, skip=False, dtype=
 
 
 def forward_hybrid(params, vol, training=False, variant="end2end", dtype=torch.float32,
-                   requires_grad=False):
-    ctx = Ctx(params, training, dtype, requires_grad)
+                   requires_grad=False, dropout_masks=None):
+    """dropout_masks: {'fianl_conv_dropout': 0/1 array in the internal (B, C, H, W, S) layout} -- see dropout()."""
+    ctx = Ctx(params, training, dtype, requires_grad, dropout_masks)
     return ctx, hybrid_net(ctx, vol, variant)
 
 

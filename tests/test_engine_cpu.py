@@ -105,6 +105,37 @@ def test_hybrid_train_step_matches_oracle(variant):
     assert rel_l2(out, l2.numpy()) < 1e-4
 
 
+def test_hybrid_train_step_with_dropout_matches_oracle():
+    """Dropout on (KB:2888, rate 0.3 after fianl_conv, hybridnet.py:415): the forward mask and the backward mask come from the
+    same stateless hash of (seed, element index); with that mask injected, the oracle's loss and gradients are the engine's."""
+    a = Args(b=1, input_size=64, input_cols=8)
+    be = TorchBackend()
+    m = hdn.dense_rnn_net(a, backend=be, device="cpu", precision="fp32")
+    assert m.dropout
+    perturb_params(m)
+    m.compile(optimizer=hdn.SGD(lr=1e-3, momentum=0.9, nesterov=True), loss=[hdn.weighted_crossentropy])
+    vol, lab = synthetic_slab(1, 64, 8)
+    w0 = m.get_weights_dict()
+    loss = m.train_on_batch(vol, lab)
+    assert len(be.masks) == 1                                  # one dropout site in the end2end graph
+    mask = be.masks[0]                                         # (N, S, H, W, C)
+    assert abs(float((mask == 0).float().mean()) - 0.3) < 0.02
+    om = {"fianl_conv_dropout": mask.permute(0, 4, 2, 3, 1).numpy()}         # oracle layout (B, C, H, W, S)
+    og = {}
+    for dt in (torch.float32, torch.float64):
+        ctx, logits = orc.forward_hybrid(w0, vol, training=True, requires_grad=True, dtype=dt, dropout_masks=om)
+        oloss = orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), logits, crop=True)
+        og[dt] = orc.grads_of(ctx, oloss)
+        if dt == torch.float32:
+            oloss32 = float(oloss)
+    assert abs(loss - oloss32) <= 1e-4 * abs(oloss32)
+    # and the masked run differs from the unmasked one (the mask is really applied)
+    _, l_nomask = orc.forward_hybrid(w0, vol, training=True)
+    assert abs(float(orc.weighted_crossentropy(torch.as_tensor(lab[..., 0]), l_nomask, crop=True)) - oloss32) > 1e-4 * abs(oloss32)
+    trainable = sorted(p.name for p in m.params.order if p.trainable)
+    _check_grads(m.get_grads_dict(), og[torch.float32], og[torch.float64], names=trainable, floor=5e-3)
+
+
 def test_net3d_matches_oracle():
     a = Args(b=1, input_size=32, input_cols=8)
     m = hdn.DenseNet3D(a, backend=TorchBackend(), device="cpu", precision="fp32")

@@ -8,6 +8,7 @@ Two uses, both inside tests/:
     of the same op").
 The product package never imports this module; without libhdn.so the product raises.
 """
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -47,11 +48,25 @@ def _conv_w(d):
     return d.w.permute(4, 3, 0, 1, 2)
 
 
+def drop_scale(seed, n, keep):
+    """hdn_drop_scale(seed, idx, keep) for idx = 0..n-1 (dense element index of the [M, C] output), restated from
+    csrc/hdn_common.cuh: a splitmix-style 64-bit hash, its top 24 bits as a uniform in [0, 1), scale = 1/keep where u < keep."""
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed) * np.uint64(0x100000001B3) + np.arange(n, dtype=np.uint64)
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        x = x ^ (x >> np.uint64(31))
+    u = ((x >> np.uint64(32)).astype(np.uint32) >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return torch.from_numpy(np.where(u < np.float32(keep), np.float32(1.0) / np.float32(keep), np.float32(0.0)).astype(np.float32))
+
+
 class TorchBackend(object):
     name = "torch-reference"
 
     def __init__(self):
         self.launches = 0
+        self.masks = []           # 0/1 dropout masks of the forward pass, in call order, engine layout (N, D, H, W, C)
 
     def conv_tc_supported(self, d, which):
         return False
@@ -64,11 +79,14 @@ class TorchBackend(object):
         return a
 
     def conv_fprop(self, d):
-        assert d.drop_keep == 1.0, "the torch reference backend has no dropout mask"
         y = F.conv3d(_cf(self._A(d)), _conv_w(d), d.bias, stride=d.s, padding=d.p)
         y = _cl(y)
         o = d.out
         y = y[:, :o.D, :o.H, :o.W]
+        if d.drop_keep < 1.0:                # tf.nn.dropout (KB:2888): the engine's stateless hash mask, restated (hdn_common.cuh)
+            scale = drop_scale(d.drop_seed, y.numel(), d.drop_keep).view(y.shape)
+            self.masks.append((scale > 0).to(torch.float32))
+            y = y * scale
         _win(o).copy_(y)
         if d.stat is not None:
             yd = y.double().reshape(-1, o.C)
@@ -202,7 +220,8 @@ class TorchBackend(object):
             tgt.copy_(g)
 
     def dropout_bwd(self, view, keep, seed):
-        raise AssertionError("no dropout in the torch reference backend")
+        g = _win(view, grad=True)
+        g.mul_(drop_scale(seed, g.numel(), keep).view(g.shape))
 
     @staticmethod
     def _wce_parts(logits, labels, N, D, HW, d0, d1):

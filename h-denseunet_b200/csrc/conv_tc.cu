@@ -9,21 +9,25 @@
 // statistics, ReLU/BN backward sums) is fused into the operand producer or the epilogue.
 //
 // Persistent kernel, one CTA per SM, each CTA loops over 128 x BN output tiles (128 GEMM rows =
-// 16 x 8 output pixels of one (n, d) slice, or 128 consecutive positions for 1x1x1).
+// 16 x 8 output pixels of one (n, d) slice, or 128 consecutive positions for 1x1x1).  Every filter tap is the SAME
+// shared-memory patch (tile + halo of one depth slab, one channel block) read through a descriptor whose start address is
+// shifted by (th*PW + tw) pixels and whose 8-row-group stride is one patch row: no im2col gather, each input element is
+// staged once per tile instead of once per tap.  The kernel is instantiated per (pass, folded bf16x3, operand path):
 //
-//   warps 0-7  producers.  Stage = one channel block (64, or 32 with two sources) of the fp32 input
-//              PATCH (tile + halo) of one depth slab.  The raw fp32 patch is fetched with cp.async
-//              (16-byte copies, several stages in flight, no registers held), then transformed once:
-//              max(a*x+b, 0) (+ second source, nearest-neighbour up-sampling in the index), bf16, stored
-//              in the UMMA no-swizzle K-major layout (chunk j of 8 channels at j*LBO, pixel q at q*16 B).
-//              Every filter tap is the SAME shared-memory patch read through a descriptor whose start
-//              address is shifted by (th*PW + tw)*16 bytes and whose 8-row-group stride is PW*16 bytes:
-//              no im2col gather, each input element is loaded once per tile instead of once per tap.
-//   warp 8     weight loader: one elected thread streams pre-packed bf16 weight blocks (already in
-//              core-matrix order) with cp.async.bulk (TMA engine) on mbarriers.
-//   warp 9     MMA issuer: one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into one of two
-//              TMEM accumulator buffers and releases stages with tcgen05.commit.
-//   warps 10-13 epilogue: tcgen05.ld the finished accumulator while the next tile's MMAs run.
+// TMA forms (every stride-1 layer; 512 threads).  The A operand was written as bf16 (head, and tail for bf16x3) by the
+// pre-pass of conv_tc2_wgrad.cu -- max(a*x+b, 0) (+ second source, up-sampling in the index) on the virtual grid.
+//   warp 0      one elected lane issues cp.async.bulk.tensor tile loads of the patch (zero padding, image borders and channel
+//               tails = the copy engine's out-of-bounds fill) into a 3-4 stage ring
+//   warp 1      weight loader: pre-packed bf16 weight blocks (core-matrix order) with cp.async.bulk, one copy and one
+//               full/empty barrier pair per filter ROW (3-4 taps)
+//   warp 2      MMA issuer (+ TMEM owner): all lanes run the loop converged, the tcgen05.mma of a whole filter row and its
+//               tcgen05.commit are issued inside one elect.sync region (see the comment at the role)
+//   warps 4-15  three epilogue sets: tcgen05.ld the finished accumulator while the next tile's MMAs run; a set takes every
+//               third 32-column block
+// SIMT form (the two stride-2 stems in space-to-depth form; 448 threads).
+//   warps 0-7   producers: the raw fp32 patch is fetched with cp.async, transformed once (prologue, bf16 head / tail) and
+//               stored in the UMMA no-swizzle K-major layout (chunk j of 8 channels at j*LBO, pixel q at q*16 B)
+//   warp 8 weight loader, warp 9 MMA issuer, warps 10-13 epilogue.
 #include <cuda.h>
 #include <stdlib.h>
 #include "hdn_common.cuh"
